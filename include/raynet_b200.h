@@ -1,0 +1,221 @@
+/*
+ * raynet_b200.h -- C-ABI of the B200-native RayNet volumetric-inference hot path.
+ *
+ * Drop-in boundary: every entry point replaces one PyCUDA `prepared_call` site of the
+ * reference (paths relative to /root/reference/raynet).  Conventions:
+ *   - all pointers are DEVICE pointers (what PyCUDA passes as `.gpudata`), C-contiguous;
+ *   - the caller allocates every output;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); launches are
+ *     asynchronous on it and correct under the reference's fully synchronous usage;
+ *   - sizes that the reference text-substitutes into the CUDA source at JIT time
+ *     (raynet_fp.py:230-248) travel in an RnParams POD at launch time -- no JIT;
+ *   - return value: 0 on success, otherwise an RnStatus / cudaError_t code; the message is
+ *     available from rn_last_error().  The Python shim raises AssertionError for
+ *     RN_ERR_SHAPE (the reference asserts, raynet_fp.py:290-301) and RuntimeError else.
+ *
+ * Layouts are the reference's: ray ids are column-major pixel indices id = x*H + y
+ * (sampling_schemes.cu:5-8); ray_voxel_indices is int32 [B][M][3]; S / messages are
+ * float32 [B][M]; accumulators are float32 [Gx][Gy][Gz]; features are float32
+ * [V][H+p+1][W+p+1][F]; P is float32 [V][3][4]; P_inv float32 [4][3]; centre float32 [4].
+ */
+#ifndef RAYNET_B200_H
+#define RAYNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_ABI_VERSION 1
+
+typedef enum RnStatus {
+    RN_OK = 0,
+    RN_ERR_SHAPE = 10001,     /* a size/shape the reference would `assert` on */
+    RN_ERR_UNSUPPORTED = 10002, /* e.g. max_voxels above the compiled limit */
+    RN_ERR_CUDA = 10003       /* a CUDA runtime error; see rn_last_error() */
+} RnStatus;
+
+/* Compile-time constants of the reference's templated kernels, as run-time data.
+ * Mirrors the arguments of perform_raynet_fp (cuda_implementations/raynet_fp.py:10-21). */
+typedef struct RnParams {
+    int32_t max_voxels;    /* M: maximum number of marched voxels per ray            */
+    int32_t depth_planes;  /* D: discretisation steps along the ray                  */
+    int32_t n_views;       /* N: number of views = neighbors + 1 (reference first)   */
+    int32_t feat_dim;      /* F: feature size of the multi-view CNN                  */
+    int32_t height;        /* H: image height                                        */
+    int32_t width;         /* W: image width                                         */
+    int32_t padding;       /* zero-padding of the CNN input (generation_parameters)  */
+    int32_t grid[3];       /* voxel grid shape (Gx, Gy, Gz)                          */
+    float bbox[6];         /* (min_x, min_y, min_z, max_x, max_y, max_z), float32    */
+} RnParams;
+
+const char *rn_last_error(void);
+int rn_abi_version(void);
+/* Number of SMs / name of the current device (diagnostics for bench.py). */
+int rn_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage-wise entry points (one per reference kernel)
+ * ------------------------------------------------------------------------------------- */
+
+/* sample_in_bbox for a batch of rays: ray start / end on the bbox.
+ * Replaces the device function sampling_schemes.cu:44-90 (no stand-alone kernel in the
+ * reference; exposed because every fused kernel starts with it).
+ * out: starts, ends float32 [n][3]. */
+int rn_sample_in_bbox(const RnParams *p, const int32_t *ray_idxs, const float *P_inv, const float *centre,
+                      float *starts, float *ends, int64_t n_rays, void *stream);
+
+/* batch_sample_points_in_bbox (sampling_schemes.cu:92-122; wrapped by
+ * cuda_implementations/sample_points.py:12-54): D uniformly spaced homogeneous points
+ * per ray.  out: points float32 [n][D][4]. */
+int rn_sample_points(const RnParams *p, const int32_t *ray_idxs, const float *P_inv, const float *centre,
+                     float *points, int64_t n_rays, void *stream);
+
+/* batch_compute_similarities (feature_similarities.cu:126-146): per-ray softmax depth
+ * distribution over D planes from V feature maps.  out: S float32 [n][D] (overwritten;
+ * the reference accumulates into a pre-zeroed S, forward_pass.py:320). */
+int rn_similarity(const RnParams *p, const float *features, const float *P, const float *starts,
+                  const float *ends, float *S, int64_t n_rays, void *stream);
+
+/* batch_multi_view_cnn_forward_pass (similarities.py:46-79): sample_in_bbox + similarity. */
+int rn_mvcnn_forward(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
+                     const float *P_inv, const float *centre, float *S, int64_t n_rays, void *stream);
+
+/* batch_multi_view_cnn_forward_pass_with_depth (similarities.py:168-230): additionally the
+ * D points per ray and depth_map[r] = |point[argmax S] - centre|.
+ * out: S [n][D], points [n][D][4], depth_map [n]. */
+int rn_mvcnn_forward_depth(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
+                           const float *P_inv, const float *centre, float *S, float *points,
+                           float *depth_map, int64_t n_rays, void *stream);
+
+/* batch_voxel_traversal (ray_tracing.cu:145-163; wrapped by ray_marching/ray_tracing_cuda.py:12-63).
+ * Arithmetic follows the Cython flavour ray_tracing.pyx:99-199 (run-time float32 bbox).
+ * out: ray_voxel_indices int32 [n][M][3] (only the first count triplets are written),
+ *      ray_voxel_count int32 [n] (always written, 0 for rays starting outside). */
+int rn_voxel_traversal(const RnParams *p, const float *starts, const float *ends, int32_t *ray_voxel_indices,
+                       int32_t *ray_voxel_count, int64_t n_rays, void *stream);
+
+/* batch_planes_voxels_mapping (planes_voxels_mapping.cu:94-118; wrapped by
+ * planes_voxels_mapping/planes_voxels_mapping_cuda.py:11-67).
+ * voxel_grid float32 [Gx][Gy][Gz][3] exactly as the reference passes it.
+ * out: S_new float32 [n][M] (first count entries written). */
+int rn_planes_to_voxels(const RnParams *p, const float *voxel_grid, const int32_t *ray_voxel_indices,
+                        const int32_t *ray_voxel_count, const float *starts, const float *ends, const float *S,
+                        float *S_new, int64_t n_rays, void *stream);
+
+/* batch_belief_propagation (mrf_bp.cu:180-204; wrapped by mrf/mrf_cuda.py:37-79): one
+ * synchronous sweep.  Reads acc_in + msgs, writes msgs IN PLACE (every reference caller
+ * aliases in/out, mrf_cuda.py:73-75) and atomically adds the new messages into acc_out.
+ * Follows mrf_np.py: S is clipped/renormalised on the fly and NOT modified; rays with
+ * count <= 1 are skipped (mrf_np.py:299-301). */
+int rn_bp_iteration(const RnParams *p, const float *S, const int32_t *ray_voxel_indices,
+                    const int32_t *ray_voxel_count, const float *acc_in, float *msgs, float *acc_out,
+                    int64_t n_rays, void *stream);
+
+/* batch_depth_estimation (mrf_bp.cu:206-228; mrf_cuda.py:81-122): S_new float32 [n][M];
+ * entries >= count and rays with count <= 1 are set to 0 (mrf_np.py:370-383). */
+int rn_depth_estimate(const RnParams *p, const float *S, const int32_t *ray_voxel_indices,
+                      const int32_t *ray_voxel_count, const float *acc, const float *msgs, float *S_new,
+                      int64_t n_rays, void *stream);
+
+/* compute_occupancy_probabilities (mrf_np.py:206-240): out[i] = sigmoid(acc[i]). */
+int rn_occupancy(const float *acc, float *out, int64_t n, void *stream);
+
+/* GPUArray.fill replacement used between sweeps (forward_pass.py:676-678). */
+int rn_fill_f32(float *dst, float value, int64_t n, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused entry points (the reference's hot kernels)
+ * ------------------------------------------------------------------------------------- */
+
+/* batch_raynet_fp (raynet_fp.py:106-149): sample -> similarity -> DDA -> plane->voxel ->
+ * one BP sweep.  Fills ray_voxel_indices, ray_voxel_count, S_voxel_space (the reference's
+ * scratch outputs), updates msgs in place and adds into acc_out. */
+int rn_raynet_fp(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
+                 const float *P_inv, const float *centre, const float *voxel_grid,
+                 int32_t *ray_voxel_indices, int32_t *ray_voxel_count, float *S_voxel_space,
+                 const float *acc_in, float *msgs, float *acc_out, int64_t n_rays, void *stream);
+
+/* batch_complete_depth_estimation (raynet_fp.py:151-227): same front end -> depth
+ * re-estimation (written over S_voxel_space) -> arg-max voxel -> distance to the camera.
+ * out: depth_map float32 [n]. */
+int rn_raynet_de(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
+                 const float *P_inv, const float *centre, const float *voxel_grid,
+                 int32_t *ray_voxel_indices, int32_t *ray_voxel_count, float *S_voxel_space,
+                 const float *acc, const float *msgs, float *depth_map, int64_t n_rays, void *stream);
+
+/* batch_mvcnn_planes_voxels_with_ray_marching
+ * (mvcnn_with_ray_marching_and_voxels_mapping.py:56-111): front end only; S_new [n][M]. */
+int rn_mvcnn_voxel(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
+                   const float *P_inv, const float *centre, const float *voxel_grid,
+                   int32_t *ray_voxel_indices, int32_t *ray_voxel_count, float *S_new, int64_t n_rays,
+                   void *stream);
+
+/* ..._with_depth (same file :222-313): + arg-max voxel over all M slots -> depth_map [n]. */
+int rn_mvcnn_voxel_depth(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
+                         const float *P_inv, const float *centre, const float *voxel_grid,
+                         int32_t *ray_voxel_indices, int32_t *ray_voxel_count, float *S_new,
+                         float *depth_map, int64_t n_rays, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Resident pipeline (B200-native state; no reference equivalent -- it replaces the host
+ * loop of RayNetForwardPass.forward_pass, forward_pass.py:593-748, which re-runs the
+ * front end and bounces messages through host memory on every sweep).
+ *
+ * Per-ray state kept in HBM between sweeps:
+ *   ray_hdr   uint32 [n][2]  first voxel + step signs      (8 B / ray)
+ *   codes     uint8  [n][code_stride]  2-bit axis code per traversed voxel (0.25 B / voxel)
+ *   count     int32  [n]
+ *   s_hat     float32 [n][M]  clip_and_renorm(S_voxel_space[r, :count])  (mrf_np.py:4-8)
+ *   msgs      float32 [n][M]
+ * rn_code_stride(M) gives the byte stride of one ray's code row.
+ * ------------------------------------------------------------------------------------- */
+int64_t rn_code_stride(int32_t max_voxels);
+
+/* Front end once per reference image: fills starts/ends (may be NULL), ray_hdr, codes,
+ * count, s_hat.  axis_centres: float32 [Gx+Gy+Gz] voxel-centre coordinates per axis
+ * (rn_axis_centres extracts them from the reference's voxel_grid table).
+ * view_ids (may be NULL): int32 [V], the slot inside `features` of each of the V views of
+ * this reference image, so that one resident feature volume [n_feature_slots][H+p+1][W+p+1][F]
+ * serves every reference image (the reference re-uploads a re-ordered copy per image,
+ * forward_pass.py:622-641).  NULL means slots 0..V-1. */
+int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *features,
+                       const int32_t *view_ids, int32_t n_feature_slots, const float *P,
+                       const float *P_inv, const float *centre, const float *axis_centres, float *starts,
+                       float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *s_hat,
+                       int64_t n_rays, void *stream);
+
+/* One BP sweep over resident state; msgs updated in place, acc_out += messages.
+ * max_count: upper bound on count[] for this launch (<= max_voxels; pass max_voxels if
+ * unknown) -- selects the register-resident ray length of the kernel. */
+int rn_engine_bp_iteration(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes,
+                           const int32_t *count, const float *s_hat, float *msgs, const float *acc_in,
+                           float *acc_out, int32_t max_count, int64_t n_rays, void *stream);
+
+/* Depth pass over resident state: depth_map[r] = |centre(voxel argmax_i o_i cp_i s_i) - C|. */
+int rn_engine_depth(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count,
+                    const float *s_hat, const float *msgs, const float *acc, const float *axis_centres,
+                    const float *centre, float *depth_map, int32_t max_count, int64_t n_rays, void *stream);
+
+/* Expand resident state into the reference's dense buffers (parity tests / debugging):
+ * ray_voxel_indices int32 [n][M][3] (zero beyond count). */
+int rn_engine_expand_indices(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes,
+                             const int32_t *count, int32_t *ray_voxel_indices, int64_t n_rays, void *stream);
+
+/* axis_centres[0:Gx] = voxel_grid[i][0][0][0], [Gx:Gx+Gy] = voxel_grid[0][j][0][1],
+ * [Gx+Gy:] = voxel_grid[0][0][k][2]  (the table of get_voxel_grid is separable,
+ * utils/generic_utils.py:104-110). */
+int rn_axis_centres(const RnParams *p, const float *voxel_grid, float *axis_centres, void *stream);
+
+/* acc[i] = prior + partial[i]: the epilogue after the NCCL all-reduce of the per-rank
+ * partial accumulators (multi-GPU path). */
+int rn_add_prior(float *acc, float prior, int64_t n, void *stream);
+
+/* max over count[0:n] written to *out_max (device int32). */
+int rn_max_count(const int32_t *count, int64_t n, int32_t *out_max, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYNET_B200_H */

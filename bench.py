@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of complete ray-potential inference (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--config c3] [--impl reference]
+    (N > 1: launched by torchrun, one rank per GPU, NCCL)
+
+One "step" = one complete inference over this rank's reference images:
+    front end (sample_in_bbox + plane-sweep similarity + DDA + plane->voxel) once per image,
+    I synchronous BP sweeps over all rays (+ one all-reduce of the occupancy accumulator per
+    sweep when N > 1), one depth pass (+ arg-max -> depth).
+`value`  : rays/s, whole job, inputs (feature maps, cameras, ray ids) resident in HBM.
+`e2e`    : the same through the reference-facing plug-in call
+           RayNetForwardPass.forward_pass(scene, images_range) with PINNED HOST feature maps in
+           and HOST depth maps out (H2D / D2H inside the timed region).
+Weak scaling: every rank owns 9 reference images (a ring of 9*N cameras; rank r owns images
+r, r+N, ... and their 8 neighbours are the same residue class), so per-GPU work is fixed.
+
+--impl reference : the CPU implementation of the path (oracle port; see cpu_baseline.kind) on
+the host cores, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: grid, views, planes, H, W, M, sweeps   
+    "c1": dict(G=32, V=2, D=16, H=64, W=64, M=96, I=3, label="C1 32^3 grid, 2 views, 16 planes, 64x64 px, 3 sweeps"),
+    "c2": dict(G=128, V=5, D=32, H=256, W=256, M=384, I=3,
+               label="C2 DTU-style 128^3 grid, 5 views, 32 planes, 256x256 px, 3 sweeps"),
+    "c3": dict(G=256, V=9, D=64, H=512, W=512, M=768, I=5,
+               label="C3 headline 256^3 grid, 9 views, 64 planes, 512x512 px, 5 sweeps"),
+}
+F, PADDING, GAMMA = 32, 11, 0.05
+METRIC = "rays/s, complete ray-potential inference (front end + I BP sweeps + depth)"
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic():
+    """dram bytes per sweep-kernel launch from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------
+def view_features(view, H, W, pinned=False):
+    """f32 [H+p+1, W+p+1, F] N(0,1)/sqrt(F), border row/col 0 zeroed; seeded by the view id."""
+    import torch
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1000 + int(view))
+    f = torch.randn((H + PADDING + 1, W + PADDING + 1, F), generator=g, dtype=torch.float32)
+    f /= float(np.sqrt(F))
+    f[0, :, :] = 0
+    f[:, 0, :] = 0
+    return f
+
+
+class FeatureModel(object):
+    """Stands for the MV-CNN (out of scope): hands out precomputed per-view feature maps that
+    live in pinned host memory, like a feature cache would."""
+
+    def __init__(self, views, H, W):
+        import torch
+        self.views = list(views)
+        self.host = torch.empty((len(self.views), H + PADDING + 1, W + PADDING + 1, F), dtype=torch.float32)
+        for k, v in enumerate(self.views):
+            self.host[k].copy_(view_features(v, H, W))
+        if torch.cuda.is_available():
+            self.host = self.host.pin_memory()
+
+    def predict_features(self, scene, view_indices):
+        if list(view_indices) == self.views:
+            return self.host
+        import torch
+        return self.host[torch.tensor([self.views.index(v) for v in view_indices])]
+
+
+def make_scene(cfg, world):
+    from raynet_b200.synth import SyntheticScene
+    n_total = cfg["V"] * world
+    return SyntheticScene(n_total, cfg["H"], cfg["W"], (cfg["G"],) * 3, neighbors=cfg["V"] - 1,
+                          neighbor_stride=world)
+
+
+def start_clock_sampler(device_index):
+    import torch
+    uuid = "GPU-" + str(torch.cuda.get_device_properties(device_index).uuid)
+    out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+        proc = subprocess.Popen(["nvidia-smi", "-i", uuid, "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                 "-lms", "50"], stdout=out, stderr=subprocess.DEVNULL)
+    except Exception:
+        return None, out.name
+    return proc, out.name
+
+
+def stop_clock_sampler(proc, path):
+    clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if proc is not None:
+        proc.terminate()
+        try:
+            proc.wait(timeout=5)
+        except Exception:
+            proc.kill()
+    try:
+        rows = [l.strip().split(", ") for l in open(path) if l.strip()]
+        sm = [float(r[0]) for r in rows if len(r) >= 8]
+        if sm:
+            clocks["sm_mhz"] = float(np.median(sm))
+            clocks["sm_max_mhz"] = float(rows[0][1])
+            clocks["power_w_max"] = max(float(r[2]) for r in rows if len(r) >= 8)
+            clocks["samples"] = len(sm)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k, nm in enumerate(names):
+                if any(r[4 + k].strip().lower() == "active" for r in rows if len(r) >= 8):
+                    clocks["reasons"].append(nm)
+    except Exception as e:
+        clocks["error"] = repr(e)
+    try:
+        os.unlink(path)
+    except OSError:
+        pass
+    return clocks
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm (oracle port): bounded sample of the same workload
+# ------------------------------------------------------------------------------------------
+class CpuSample(object):
+    def __init__(self, cfg, n_rays):
+        from oracle import oracle as orc
+        from raynet_b200.synth import camera_arrays
+        self.orc = orc
+        self.cfg = cfg
+        scene = make_scene(cfg, 1)
+        H, W = cfg["H"], cfg["W"]
+        order = scene.view_order(0)
+        self.P, self.P_inv, self.centre = camera_arrays([scene.get_image(j) for j in order])
+        self.features = np.stack([view_features(v, H, W).numpy() for v in order])
+        stride = max(1, (H * W) // n_rays)
+        self.ray_idxs = np.arange(0, H * W, stride, dtype=np.int32)[:n_rays]     # pixels spread over the image
+        self.grid = np.array([cfg["G"]] * 3, np.int32)
+        self.bbox = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+        self.vgrid = orc.voxel_grid(self.bbox, self.grid)
+
+    def step(self):
+        """front end + I sweeps + depth distribution + arg-max depth, all host threads (OpenMP)."""
+        c, orc = self.cfg, self.orc
+        t0 = time.perf_counter()
+        o = orc.frontend(self.ray_idxs, self.features, self.P, self.P_inv, self.centre, self.vgrid, self.bbox,
+                         self.grid, c["M"], c["D"], c["V"], F, c["H"], c["W"], PADDING, want_stages=False)
+        acc, msgs = orc.belief_propagation(o["S_vox"], o["idx"], o["cnt"], self.grid, gamma=GAMMA,
+                                           bp_iterations=c["I"])
+        S_new = orc.depth_distribution(o["S_vox"], o["idx"], o["cnt"], self.grid, acc, msgs)
+        orc.argmax_depth(S_new, o["idx"], self.vgrid, self.grid, self.centre)
+        return time.perf_counter() - t0
+
+
+def cpu_calibrated_sample(cfg, target_s):
+    """Pick a ray count whose step takes about target_s on this host."""
+    probe = CpuSample(cfg, 1024)
+    probe.step()
+    t = probe.step()
+    n = int(max(1024, min(cfg["H"] * cfg["W"], 1024 * target_s / max(t, 1e-4))))
+    return CpuSample(cfg, n)
+
+
+def run_reference_arm(args, cfg):
+    """--impl reference: the CPU implementation on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    cores = orc.num_threads()
+    sample = cpu_calibrated_sample(cfg, 2.0)
+    for _ in range(args.warmup):
+        sample.step()
+    times = [sample.step() for _ in range(args.steps)]
+    ms = 1e3 * float(np.mean(times))
+    n = int(sample.ray_idxs.shape[0])
+    value = n / (ms * 1e-3)
+    desc = "%d rays of reference image 0 of %s per step (strided pixels), full pipeline" % (n, cfg["label"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["label"], "rays_per_step": n, "host": "CPU only"},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": desc,
+                         "note": "OpenMP C restatement of the reference's numpy/Cython/.cu path (oracle/rn_oracle.c); "
+                                 "the reference's own CPU code is single-threaded Python loops"},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu_arm(args, cfg):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback (use --impl reference for "
+                         "the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus and rank == 0:
+        print("[bench] note: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+
+    from raynet_b200 import _lib
+    from raynet_b200.common.generation_parameters import GenerationParameters
+    from raynet_b200.engine import RayPotentialEngine
+    from raynet_b200.forward_pass import RayNetForwardPass
+    from raynet_b200.synth import camera_arrays
+    _lib.load()
+
+    H, W, G, V, D, M, I = (cfg[k] for k in ("H", "W", "G", "V", "D", "M", "I"))
+    scene = make_scene(cfg, world)
+    n_total = scene.n_images
+    my_images = list(range(rank, n_total, world))              # this rank's reference images
+    my_views = sorted(set(v for i in my_images for v in scene.view_order(i)))
+    model = FeatureModel(my_views, H, W)
+    n_rays = len(my_images) * H * W
+    dev = torch.device("cuda", local)
+
+    # ---------------- device-resident arm -------------------------------------------------------
+    eng = RayPotentialEngine(M, D, V, F, H, W, PADDING, scene.bbox.ravel(), (G, G, G), gamma=GAMMA, max_rays=n_rays)
+    eng.set_voxel_grid(scene.voxel_grid())
+    feats = model.host.to(dev)
+    slot = dict((v, k) for k, v in enumerate(my_views))
+    per_image = []
+    ids = torch.arange(H * W, dtype=torch.int32, device=dev)
+    for i in my_images:
+        order = scene.view_order(i)
+        P, P_inv, centre = camera_arrays([scene.get_image(j) for j in order])
+        per_image.append((torch.from_numpy(P).to(dev), torch.from_numpy(P_inv).to(dev),
+                          torch.from_numpy(centre).to(dev),
+                          torch.tensor([slot[v] for v in order], dtype=torch.int32, device=dev)))
+    stage_events = []
+
+    def device_step(record=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        if record:
+            ev[0].record()
+        eng.reset()
+        for (P, P_inv, centre, vids) in per_image:
+            eng.add_image(ids, feats, P, P_inv, centre, view_ids=vids, n_feature_slots=len(my_views))
+        eng.finalize_frontend()
+        if record:
+            ev[1].record()
+        eng.run_bp(I)
+        if record:
+            ev[2].record()
+        depth = eng.depth()
+        if record:
+            ev[3].record()
+            stage_events.append(ev)
+        return depth
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            fn()
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    proc, path = start_clock_sampler(local) if rank == 0 else (None, None)
+    eng.sweep_events = []
+    launches0 = eng.launches
+    ms_step = timed(lambda: device_step(record=True), args.steps)
+    gpu_launches = eng.launches - launches0
+    sweep_ms = [a.elapsed_time(b) for (a, b) in eng.sweep_events]
+    eng.sweep_events = None
+    clocks = stop_clock_sampler(proc, path) if rank == 0 else None
+    stages = np.array([[e[k].elapsed_time(e[k + 1]) for k in range(3)] for e in stage_events])
+    counts = eng.count[:eng.n_rays]
+    sum_L = int(counts[counts > 1].sum().item())
+    mean_L = float(counts.float().mean().item())
+    max_L = int(eng.max_count)
+    total_rays = n_rays * world
+    value = total_rays / (ms_step * 1e-3)
+
+    # ---------------- e2e arm: reference-facing plug-in call, host buffers --------------------------
+    gp = GenerationParameters(depth_planes=D, neighbors=V - 1, grid_shape=np.array([G, G, G], np.int32),
+                              max_number_of_marched_voxels=M, padding=PADDING, gamma_mrf=GAMMA)
+    del eng, feats
+    torch.cuda.empty_cache()
+    fp = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, rays_batch=H * W, bp_iterations=I)
+    images_range = (rank, n_total, world)
+
+    def e2e_step():
+        maps = list(fp.forward_pass(scene, images_range))
+        assert len(maps) == len(my_images) and maps[0].shape == (H, W)
+        return maps
+
+    for _ in range(2):
+        e2e_step()
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    e2e = {"value": total_rays / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(fp.h2d_bytes), "d2h_bytes_per_step": int(fp.d2h_bytes),
+           "api": "raynet_b200.forward_pass.RayNetForwardPass.forward_pass(scene, images_range), pinned host "
+                  "feature maps in, host depth maps out; host wall clock around the call"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        # dominant kernel: the BP sweep.  Algorithmic bytes per launch = 20 B per traversed voxel
+        # (s_hat 4 + msg in 4 + msg out 4 + acc gather 4 + acc scatter-add 4)
+        sweep_avg_ms = float(np.mean(sweep_ms))
+        bytes_per_launch = 20.0 * sum_L
+        achieved = bytes_per_launch / (sweep_avg_ms * 1e-3) / 1e9
+        traffic = profiled_traffic()
+        # whole-step byte model of SURVEY.md 8d, for context
+        feat_share = len(my_views) * (H + PADDING + 1) * (W + PADDING + 1) * F * 4.0
+        step_bytes = sum_L * (20.0 * I + 16.0) + 28.0 * n_rays + feat_share + I * 3 * G ** 3 * 4.0
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": cfg["label"], "rays_per_gpu": n_rays, "rays_total": total_rays,
+                "reference_images_per_gpu": len(my_images), "bp_sweeps": I, "max_voxels": M,
+                "mean_voxels_per_ray": mean_L, "longest_ray": max_L, "parallelism": "rays sharded, dp%d" % world,
+                "collective": ("all-reduce f32[%d^3] per sweep (NCCL)" % G) if world > 1 else "none",
+                "l2": "per-step working set (%.1f GB of per-ray state) is far larger than L2; no flush needed"
+                      % (2 * n_rays * M * 4 / 1e9),
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (traffic or {}).get("bp_kernel_dram_bytes_per_launch"),
+                "kernel": "bp_kernel (one BP sweep over all rays of this rank)",
+                "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": sweep_avg_ms,
+                "launches_timed": len(sweep_ms), "peak_source": peak_src,
+                "step_model": {"bytes_per_step_per_gpu": step_bytes,
+                               "frac_of_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+            },
+            "stages_ms": {"frontend": float(stages[:, 0].mean()), "bp": float(stages[:, 1].mean()),
+                          "depth": float(stages[:, 2].mean())},
+            "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as orc
+            orc.build()
+            sample = cpu_calibrated_sample(cfg, 8.0)
+            t = sample.step()
+            n = int(sample.ray_idxs.shape[0])
+            line["cpu_baseline"] = {
+                "value": n / t, "unit": "rays/s", "cores": orc.num_threads(), "kind": "port",
+                "sample": "%d rays of reference image 0 of the same workload (strided pixels), full pipeline, "
+                          "one pass of %.1f s" % (n, t)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+    else:
+        run_gpu_arm(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,7 +16,7 @@ with the prior so that the all-reduce result already is prior + sum of messages.
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from .cuda_implementations.utils import current_stream_ptr, device
 
 
@@ -69,6 +69,7 @@ class RayPotentialEngine(object):
         self._max_count_dev = torch.zeros((1,), dtype=torch.int32, **kw)
         self._axes_set = False
         self.iterations_done = 0
+        self.sweep_events = None    # bench.py: list of (start, end) CUDA events around each sweep kernel
 
     # ------------------------------------------------------------------ setup
     def set_voxel_grid(self, voxel_grid):
@@ -134,16 +135,19 @@ class RayPotentialEngine(object):
     # ------------------------------------------------------------------ BP
     def bp_iteration(self):
         st = current_stream_ptr()
-        if self.world == 1 or self.rank == 0:
-            _lib.call("rn_fill_f32", _ptr(self.acc_new), self.prior, self.G, st)
-        else:
-            _lib.call("rn_fill_f32", _ptr(self.acc_new), 0.0, self.G, st)
+        _lib.call("rn_fill_f32", _ptr(self.acc_new), sharding.seed_value(self.rank, self.prior), self.G, st)
+        if self.sweep_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         _lib.call("rn_engine_bp_iteration", self.params, _ptr(self.hdr), _ptr(self.codes), _ptr(self.count),
                   _ptr(self.s_hat), _ptr(self.msgs), _ptr(self.acc_prev), _ptr(self.acc_new),
                   int(self.max_count), self.n_rays, st)
+        if self.sweep_events is not None:
+            ev[1].record()
+            self.sweep_events.append(ev)
         self.launches += 2
         if self.world > 1:
-            torch.distributed.all_reduce(self.acc_new, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            sharding.allreduce_accumulator(self.acc_new, self.pg)
         self.acc_prev, self.acc_new = self.acc_new, self.acc_prev
         self.iterations_done += 1
 

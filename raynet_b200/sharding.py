@@ -1,0 +1,63 @@
+"""Ray sharding across GPUs (one process per GPU) -- host-side logic only, no kernels.
+
+The reference has no multi-GPU code.  The path shards because its BP is
+synchronous (Jacobi): within a sweep every ray reads only the previous accumulator and adds
+its messages into the new one (mrf_np.py:295-319), so rays can live on any rank as long as
+the per-rank partial accumulators are summed once per sweep.
+
+  * rays are enumerated in (reference image, column-major pixel) order and cut into `world`
+    contiguous blocks, so each rank's rays stay spatially coherent;
+  * every rank accumulates into a partial grid seeded with `seed_value(rank, prior)`: the
+    prior on rank 0 and zero elsewhere, so that the SUM all-reduce directly yields
+    prior + sum of all messages -- no epilogue pass over the grid;
+  * `allreduce_accumulator` is the one collective of the path.
+
+This module is what the world_size-2 gloo tests exercise on CPU.
+"""
+import torch
+
+
+def ray_block(n_rays, rank, world):
+    """Half-open [start, stop) of the contiguous block of `n_rays` owned by `rank`.
+    Blocks differ by at most one ray; every ray is owned exactly once."""
+    n_rays, rank, world = int(n_rays), int(rank), int(world)
+    assert world >= 1 and 0 <= rank < world and n_rays >= 0
+    base, extra = divmod(n_rays, world)
+    start = rank * base + min(rank, extra)
+    stop = start + base + (1 if rank < extra else 0)
+    return start, stop
+
+
+def image_segments(rays_per_image, rank, world):
+    """Split the concatenation of the images' ray lists into `world` contiguous blocks and
+    return this rank's pieces as [(image_position, first, last_exclusive), ...] where first /
+    last index into that image's ray list.  `rays_per_image`: list of ints."""
+    total = int(sum(rays_per_image))
+    start, stop = ray_block(total, rank, world)
+    out, off = [], 0
+    for k, n in enumerate(rays_per_image):
+        a, b = max(start, off), min(stop, off + n)
+        if b > a:
+            out.append((k, a - off, b - off))
+        off += n
+    return out
+
+
+def images_of_rank(n_images, rank, world):
+    """Weak-scaling layout: whole reference images dealt out in contiguous runs."""
+    start, stop = ray_block(n_images, rank, world)
+    return list(range(start, stop))
+
+
+def seed_value(rank, prior):
+    """Initial value of a rank's partial accumulator (see module docstring)."""
+    return float(prior) if int(rank) == 0 else 0.0
+
+
+def allreduce_accumulator(acc, group=None):
+    """Sum the per-rank partial accumulators in place (NCCL over NVLink on the GPUs; gloo in
+    the CPU tests).  No-op outside a process group."""
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        if torch.distributed.get_world_size(group) > 1:
+            torch.distributed.all_reduce(acc, op=torch.distributed.ReduceOp.SUM, group=group)
+    return acc

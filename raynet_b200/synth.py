@@ -97,15 +97,17 @@ def random_features(n_views, H, W, F, padding, seed=0):
 class SyntheticScene(object):
     """Duck type of raynet.common.scene.Scene for the forward passes: image_shape, bbox,
     voxel_grid(), get_image(), get_image_with_neighbors().  Every view is a reference view
-    in turn with the next `neighbors` views of the ring as its neighbours."""
+    in turn with the next `neighbors` views of the ring (every `neighbor_stride`-th one) as its
+    neighbours."""
 
     def __init__(self, n_views, H, W, grid_shape, bbox=(-1, -1, -1, 1, 1, 1), neighbors=None, with_images=False,
-                 seed=0):
+                 seed=0, neighbor_stride=1):
         self.n_views = n_views
         self._H, self._W = H, W
         self.grid_shape = np.asarray(grid_shape, dtype=np.int32)
         self._bbox = np.asarray(bbox, dtype=np.float32).reshape(1, 6)
         self.neighbors = (n_views - 1) if neighbors is None else neighbors
+        self.neighbor_stride = int(neighbor_stride)
         cams = ring_cameras(n_views, H, W)
         rng = np.random.RandomState(seed)
         self.images = [Image(c, rng.rand(H, W, 3).astype(np.float32) if with_images else None) for c in cams]
@@ -132,7 +134,7 @@ class SyntheticScene(object):
         return self.images[i]
 
     def view_order(self, i):
-        return [(i + k) % self.n_views for k in range(self.neighbors + 1)]
+        return [(i + k * self.neighbor_stride) % self.n_views for k in range(self.neighbors + 1)]
 
     def get_image_with_neighbors(self, i):
         return [self.images[j] for j in self.view_order(i)]

@@ -1,0 +1,50 @@
+"""Shared synthetic cases for the parity tests.  Pure numpy; no GPU, no oracle."""
+import numpy as np
+
+from raynet_b200.synth import SyntheticScene, camera_arrays, get_voxel_grid, random_features
+
+PADDING = 11
+F = 32
+
+
+class Case(object):
+    """One reference image of the synthetic ring rig with everything the kernels consume."""
+
+    def __init__(self, G, V, D, H, W, M, n_rays=None, ref_idx=0, seed=0, bbox=(-1, -1, -1, 1, 1, 1), grid=None):
+        self.G, self.V, self.D, self.H, self.W, self.M = G, V, D, H, W, M
+        self.grid = np.asarray(grid if grid is not None else (G, G, G), np.int32)
+        self.bbox = np.asarray(bbox, np.float32)
+        self.scene = SyntheticScene(V, H, W, self.grid, bbox=bbox)
+        self.features_all = random_features(V, H, W, F, PADDING, seed=seed)      # slot v = view v
+        self.vgrid = np.ascontiguousarray(get_voxel_grid(self.bbox, self.grid).transpose(1, 2, 3, 0))
+        self.set_reference(ref_idx, n_rays, seed)
+
+    def set_reference(self, ref_idx, n_rays=None, seed=0):
+        self.ref_idx = ref_idx
+        order = self.scene.view_order(ref_idx)
+        self.view_ids = np.asarray(order, np.int32)
+        images = [self.scene.get_image(j) for j in order]
+        self.P, self.P_inv, self.centre = camera_arrays(images)
+        self.features = np.ascontiguousarray(self.features_all[order])             # reference's re-ordered copy
+        if n_rays is None or n_rays >= self.H * self.W:
+            self.ray_idxs = np.arange(self.H * self.W, dtype=np.int32)
+        else:
+            rng = np.random.default_rng(seed)
+            self.ray_idxs = np.sort(rng.choice(self.H * self.W, size=n_rays, replace=False)).astype(np.int32)
+        self.N = self.ray_idxs.shape[0]
+        return self
+
+
+def case_c1(**kw):
+    """C1: 32^3 grid, 2 views, 16 planes, 1000 rays of a 64x64 image, M=96."""
+    return Case(32, 2, 16, 64, 64, 96, n_rays=1000, **kw)
+
+
+def case_small(**kw):
+    """A 5-view / 32-plane case with rays long enough to span several 128-voxel chunks."""
+    return Case(96, 5, 32, 48, 40, 288, n_rays=1200, **kw)
+
+
+def sigmoid(x):
+    x = np.asarray(x, np.float64)
+    return 1.0 / (1.0 + np.exp(-x))

@@ -1,0 +1,154 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol of include/raynet_b200.h, the
+host logic (parameter block, ray sharding, error mapping) behaves, the product never touches
+oracle/, and the N>1 path (ray blocks + one SUM all-reduce per sweep) reproduces the
+single-process result over a world_size-2 gloo group.  No kernel is launched here.
+"""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "raynet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    from raynet_b200 import _lib, build
+    build.build()                                  # nvcc cross-compiles without a GPU
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), "symbol %s declared in the header is not exported" % s
+    # and the ctypes table covers the header exactly
+    assert sorted(list(_lib.SIGNATURES) + _lib.OTHER_SYMBOLS) == syms
+    assert lib.rn_abi_version() == 1
+    assert lib.rn_code_stride(768) == 192 and lib.rn_code_stride(96) == 32 and lib.rn_code_stride(1) == 32
+
+
+def test_params_struct_layout_matches_header():
+    from raynet_b200 import _lib
+    p = _lib.make_params(768, 64, 9, 32, 512, 512, 11, [-1, -1, -1, 1, 1, 1], [256, 256, 256])
+    assert ctypes.sizeof(p) == 4 * 10 + 4 * 6
+    assert (p.max_voxels, p.depth_planes, p.n_views, p.feat_dim, p.height, p.width, p.padding) == \
+        (768, 64, 9, 32, 512, 512, 11)
+    assert list(p.grid) == [256, 256, 256] and list(p.bbox) == [-1, -1, -1, 1, 1, 1]
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from raynet_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.RayNetB200Error):
+        _lib.load()
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from raynet_b200.cuda_implementations.utils import device
+    with pytest.raises(RuntimeError):
+        device()
+    from raynet_b200.mrf.bp_inference import get_bp_backend
+    with pytest.raises(NotImplementedError):
+        get_bp_backend("numpy", None)
+    from raynet_b200.ray_marching.ray_marching import get_voxel_traversal_backend
+    with pytest.raises(NotImplementedError):
+        get_voxel_traversal_backend("cython")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "raynet_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "rn_oracle" not in src and "liboracle" not in src, f
+
+
+def test_ray_blocks_partition():
+    from raynet_b200 import sharding
+    for n in (0, 1, 7, 8, 2359296, 1000003):
+        for world in (1, 2, 3, 8):
+            blocks = [sharding.ray_block(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    segs = [sharding.image_segments([10, 10, 10], r, 4) for r in range(4)]
+    covered = sorted((k, i) for s in segs for (k, a, b) in s for i in range(a, b))
+    assert covered == [(k, i) for k in range(3) for i in range(10)]
+    assert sharding.images_of_rank(72, 3, 8) == list(range(27, 36))
+    assert sharding.seed_value(0, -2.5) == -2.5 and sharding.seed_value(3, -2.5) == 0.0
+
+
+def test_generation_parameters_from_options():
+    import argparse
+    from raynet_b200.common.generation_parameters import GenerationParameters
+    ns = argparse.Namespace(patch_shape=(11, 11, 3), depth_planes=32, neighbors=4, grid_shape=(256, 256, 128),
+                            maximum_number_of_marched_voxels=650, depth_range=None, step_depth=None, padding=None,
+                            initial_gamma_prior=0.05)
+    gp = GenerationParameters.from_options(ns)
+    assert gp.padding == 11 and gp.max_number_of_marched_voxels == 650 and gp.gamma_mrf == 0.05
+    assert gp.depth_planes == 32 and gp.neighbors == 4
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+from oracle import oracle as orc
+from raynet_b200 import sharding
+from rig import case_c1
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+c = case_c1()
+o = orc.frontend(c.ray_idxs, c.features, c.P, c.P_inv, c.centre, c.vgrid, c.bbox, c.grid, c.M, c.D, c.V, 32,
+                 c.H, c.W, 11)
+prior = np.float32(np.log(0.05) - np.log(1 - 0.05))
+a, b = sharding.ray_block(c.N, rank, world)
+S, idx, cnt = o["S_vox"][a:b], o["idx"][a:b], o["cnt"][a:b]
+acc_prev = np.full(tuple(c.grid), prior, np.float32)
+msgs = np.zeros((b - a, c.M), np.float32)
+for it in range(3):
+    part = np.full(tuple(c.grid), sharding.seed_value(rank, prior), np.float32)
+    orc.bp_iteration(S, idx, cnt, c.grid, acc_prev, part, msgs)
+    t = torch.from_numpy(part)
+    sharding.allreduce_accumulator(t)
+    acc_prev = t.numpy().copy()
+if rank == 0:
+    ref_acc, ref_msgs = orc.belief_propagation(o["S_vox"], o["idx"], o["cnt"], c.grid, gamma=0.05, bp_iterations=3)
+    err = np.abs(orc.occupancy(acc_prev) - orc.occupancy(ref_acc)).max()
+    merr = np.abs(msgs - ref_msgs[a:b]).max()
+    print("RESULT %.3e %.3e" % (err, merr))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_sharded_bp_matches_single_process(tmp_path, oracle):
+    """world_size 2 over gloo on CPU: each rank owns a contiguous ray block, partial
+    accumulators are seeded (prior on rank 0, zero elsewhere) and summed with the product's
+    all-reduce helper after every sweep; the oracle stands in for the kernels.  The result must
+    equal the single-process oracle run (summation order differs -> tolerance, not equality)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = [l for l in outs[0].splitlines() if l.startswith("RESULT")][0]
+    err, merr = (float(x) for x in line.split()[1:])
+    assert err <= 1e-5 and merr <= 1e-3

@@ -1,0 +1,558 @@
+"""GPU parity tests: the sm_100a kernels, called through the C-ABI (include/raynet_b200.h), against
+the CPU oracle (oracle/rn_oracle.c) and the committed reference fixtures (tests/golden/).
+
+Gates (BASELINE.json north_star / SURVEY.md 8d):
+  * ray-voxel index lists and counts: BIT-EXACT;
+  * depth / occupancy marginals (probabilities): |delta| <= 1e-5 absolute, one sweep at a time
+    from identical state (tolerance TOL_P below); multi-sweep gates state their own bound,
+    because the reference's own float32- and float64-accumulator flavours already differ by
+    ~2e-5 after a few sweeps ("hard parts").
+"""
+import numpy as np
+import pytest
+
+from rig import Case, case_c1, case_small, sigmoid
+
+pytestmark = pytest.mark.gpu
+
+TOL_P = 1e-5          # absolute tolerance on probabilities (north star)
+PRIOR = float(np.float32(np.log(0.05) - np.log(1 - 0.05)))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "the gpu-marked tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from raynet_b200 import _lib
+    _lib.load()        # raises if the .so is missing: there is no fallback
+    return _lib
+
+
+def _d(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _stream(torch):
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _params(lib, c, M=None):
+    return lib.make_params(M if M is not None else c.M, c.D, c.V, 32, c.H, c.W, 11, c.bbox, c.grid)
+
+
+def _oracle_frontend(oracle, c):
+    return oracle.frontend(c.ray_idxs, c.features, c.P, c.P_inv, c.centre, c.vgrid, c.bbox, c.grid, c.M, c.D,
+                           c.V, 32, c.H, c.W, 11)
+
+
+# ----------------------------------------------------------------------------- a3: DDA
+def test_dda_golden_fixture_bit_exact(torch_cuda, lib):
+    """rn_voxel_traversal vs the reference's Cython DDA output committed in tests/golden/."""
+    import os
+    torch = torch_cuda
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+    for ci in range(3):
+        bbox, grid = g["dda%d_bbox" % ci], g["dda%d_grid" % ci]
+        ref_idx, ref_cnt = g["dda%d_idx" % ci], g["dda%d_cnt" % ci]
+        n, M, _ = ref_idx.shape
+        p = lib.make_params(M=M, bbox=bbox, grid_shape=grid)
+        idx = torch.zeros((n, M, 3), dtype=torch.int32, device="cuda")
+        cnt = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+        lib.call("rn_voxel_traversal", p, _d(torch, g["dda%d_starts" % ci]).data_ptr(),
+                 _d(torch, g["dda%d_ends" % ci]).data_ptr(), idx.data_ptr(), cnt.data_ptr(), n, _stream(torch))
+        assert np.array_equal(cnt.cpu().numpy(), ref_cnt)
+        assert np.array_equal(idx.cpu().numpy(), ref_idx)
+
+
+def test_dda_reference_unit_tests(torch_cuda):
+    """The reference's tests/test_ray_marching.py:20-77 replayed through the drop-in
+    ray_tracing_cuda.voxel_traversal (same signature as the Cython function)."""
+    from raynet_b200.ray_marching.ray_tracing_cuda import voxel_traversal
+    bbox = np.array([3, 3, 0, 6, 6, 1], np.float32)
+    grid = np.array([3, 3, 1], np.int32)
+    for s, e, n_expect in (([3., 4.1, .5], [6., 4.9, .5], 3), ([4., 6., .5], [6., 5., .5], 2),
+                           ([3., 3., .5], [6., 6., .5], 5), ([6., 6., .5], [3., 3., .5], 5)):
+        v = np.zeros((10, 3), np.int32)
+        assert voxel_traversal(bbox, grid, v, np.array(s, np.float32), np.array(e, np.float32)) == n_expect
+    v = np.zeros((10, 3), np.int32)
+    n = voxel_traversal(np.array([0, 0, 0, 6, 6, 1], np.float32), np.array([6, 6, 1], np.int32), v,
+                        np.array([0., 3.5, .5], np.float32), np.array([6., .5, .5], np.float32))
+    assert n == 9
+    expect = np.array([[0, 3, 0], [0, 2, 0], [1, 2, 0], [2, 2, 0], [2, 1, 0], [3, 1, 0], [4, 1, 0], [4, 0, 0],
+                       [5, 0, 0], [0, 0, 0]])
+    assert np.array_equal(v, expect)
+
+
+@pytest.mark.parametrize("G,H,W,M", [(32, 64, 64, 96), (128, 96, 80, 384), (256, 64, 48, 768)])
+def test_dda_rig_bit_exact_and_codes(torch_cuda, lib, oracle, G, H, W, M):
+    """All rays of one rig image: sample_in_bbox on the GPU, then (i) reference-layout lists
+    and (ii) the resident 2-bit step codes expanded again, both bit-equal to the oracle DDA fed
+    with the same float32 start/end."""
+    torch = torch_cuda
+    c = Case(G, 3, 8, H, W, M)
+    p = _params(lib, c)
+    ids = _d(torch, c.ray_idxs)
+    Pinv, C = _d(torch, c.P_inv), _d(torch, c.centre)
+    starts = torch.empty((c.N, 3), dtype=torch.float32, device="cuda")
+    ends = torch.empty_like(starts)
+    lib.call("rn_sample_in_bbox", p, ids.data_ptr(), Pinv.data_ptr(), C.data_ptr(), starts.data_ptr(),
+             ends.data_ptr(), c.N, _stream(torch))
+    o_s, o_e = oracle.sample_in_bbox(c.ray_idxs, c.H, c.P_inv, c.centre, c.bbox)
+    # a1 is IEEE f32/f64 arithmetic in the same order on both sides
+    assert np.array_equal(starts.cpu().numpy(), o_s) and np.array_equal(ends.cpu().numpy(), o_e)
+    idx = torch.zeros((c.N, M, 3), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros((c.N,), dtype=torch.int32, device="cuda")
+    lib.call("rn_voxel_traversal", p, starts.data_ptr(), ends.data_ptr(), idx.data_ptr(), cnt.data_ptr(), c.N,
+             _stream(torch))
+    o_idx, o_cnt = oracle.voxel_traversal(c.bbox, c.grid, o_s, o_e, M)
+    assert np.array_equal(cnt.cpu().numpy(), o_cnt)
+    assert np.array_equal(idx.cpu().numpy(), o_idx)
+    assert o_cnt.max() > G          # the rig really produces long rays
+    # resident codes
+    from raynet_b200.engine import RayPotentialEngine
+    eng = RayPotentialEngine(M, c.D, c.V, 32, c.H, c.W, 11, c.bbox, c.grid, max_rays=c.N, use_distributed=False)
+    eng.set_voxel_grid(c.vgrid)
+    eng.add_image(ids, _d(torch, c.features), _d(torch, c.P), Pinv, C)
+    assert np.array_equal(eng.count.cpu().numpy(), o_cnt)
+    assert np.array_equal(eng.voxel_indices().cpu().numpy(), o_idx)
+
+
+def test_dda_truncation_and_misses(torch_cuda, lib, oracle):
+    """M smaller than the ray (silent truncation, ray_tracing.cu:100) and rays that miss the
+    box (count 0, nothing written)."""
+    torch = torch_cuda
+    bbox = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    grid = np.array([64, 64, 64], np.int32)
+    rng = np.random.RandomState(3)
+    n, M = 500, 40
+    starts = (rng.rand(n, 3) * 2 - 1).astype(np.float32)
+    ends = (rng.rand(n, 3) * 2 - 1).astype(np.float32)
+    starts[:50] += 3.0                                         # start outside -> count 0
+    starts[50:60, 0] = ends[50:60, 0]                          # a zero direction component
+    p = lib.make_params(M=M, bbox=bbox, grid_shape=grid)
+    idx = torch.full((n, M, 3), -7, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros((n,), dtype=torch.int32, device="cuda")
+    lib.call("rn_voxel_traversal", p, _d(torch, starts).data_ptr(), _d(torch, ends).data_ptr(), idx.data_ptr(),
+             cnt.data_ptr(), n, _stream(torch))
+    o_idx, o_cnt = oracle.voxel_traversal(bbox, grid, starts, ends, M)
+    cnt, idx = cnt.cpu().numpy(), idx.cpu().numpy()
+    assert np.array_equal(cnt, o_cnt)
+    assert (o_cnt == M).any() and (o_cnt[:50] == 0).all()
+    for r in range(n):
+        assert np.array_equal(idx[r, :cnt[r]], o_idx[r, :cnt[r]])
+        assert (idx[r, cnt[r]:] == -7).all()                   # nothing written beyond count
+
+
+# ----------------------------------------------------------------------------- a2: similarity
+@pytest.mark.parametrize("mk", [case_c1, case_small])
+def test_similarity_vs_oracle(torch_cuda, lib, oracle, mk):
+    torch = torch_cuda
+    c = mk()
+    p = _params(lib, c)
+    S = torch.full((c.N, c.D), -1.0, dtype=torch.float32, device="cuda")
+    lib.call("rn_mvcnn_forward", p, _d(torch, c.ray_idxs).data_ptr(), _d(torch, c.features).data_ptr(),
+             _d(torch, c.P).data_ptr(), _d(torch, c.P_inv).data_ptr(), _d(torch, c.centre).data_ptr(),
+             S.data_ptr(), c.N, _stream(torch))
+    o = _oracle_frontend(oracle, c)
+    S = S.cpu().numpy()
+    assert np.abs(S - o["S"]).max() <= TOL_P
+    assert np.abs(S.sum(1) - 1).max() < 1e-5
+    assert (o["S"].max(1) > 2.0 / c.D).any()                  # not a flat distribution
+    # stand-alone similarity on given start/end
+    S2 = torch.zeros((c.N, c.D), dtype=torch.float32, device="cuda")
+    lib.call("rn_similarity", p, _d(torch, c.features).data_ptr(), _d(torch, c.P).data_ptr(),
+             _d(torch, o["starts"]).data_ptr(), _d(torch, o["ends"]).data_ptr(), S2.data_ptr(), c.N,
+             _stream(torch))
+    assert np.array_equal(S2.cpu().numpy(), S)
+
+
+def test_similarity_with_depth_and_points(torch_cuda, lib, oracle):
+    """rn_mvcnn_forward_depth: D points per ray + |point[argmax S] - C| (similarities.py:168-230)."""
+    torch = torch_cuda
+    c = case_small()
+    p = _params(lib, c)
+    S = torch.zeros((c.N, c.D), dtype=torch.float32, device="cuda")
+    pts = torch.zeros((c.N, c.D, 4), dtype=torch.float32, device="cuda")
+    depth = torch.zeros((c.N,), dtype=torch.float32, device="cuda")
+    lib.call("rn_mvcnn_forward_depth", p, _d(torch, c.ray_idxs).data_ptr(), _d(torch, c.features).data_ptr(),
+             _d(torch, c.P).data_ptr(), _d(torch, c.P_inv).data_ptr(), _d(torch, c.centre).data_ptr(),
+             S.data_ptr(), pts.data_ptr(), depth.data_ptr(), c.N, _stream(torch))
+    o = _oracle_frontend(oracle, c)
+    S, pts, depth = S.cpu().numpy(), pts.cpu().numpy(), depth.cpu().numpy()
+    k = np.arange(c.D, dtype=np.float32)[None, :, None]
+    ref_pts = o["starts"][:, None, :] + k * (o["ends"] - o["starts"])[:, None, :] / np.float32(c.D - 1)
+    assert np.array_equal(pts[:, :, :3], ref_pts.astype(np.float32)) and (pts[:, :, 3] == 1).all()
+    am = S.argmax(1)
+    ref_depth = np.sqrt(((pts[np.arange(c.N), am, :3] - c.centre[:3]) ** 2).sum(1))
+    assert np.abs(depth - ref_depth).max() < 1e-5
+    # sample_points drop-in gives the same points
+    pts2 = torch.zeros((c.N, c.D, 4), dtype=torch.float32, device="cuda")
+    lib.call("rn_sample_points", p, _d(torch, c.ray_idxs).data_ptr(), _d(torch, c.P_inv).data_ptr(),
+             _d(torch, c.centre).data_ptr(), pts2.data_ptr(), c.N, _stream(torch))
+    assert np.array_equal(pts2.cpu().numpy(), pts)
+
+
+# ----------------------------------------------------------------------------- a4: plane -> voxel
+@pytest.mark.parametrize("mk", [case_c1, case_small])
+def test_planes_to_voxels_vs_oracle(torch_cuda, lib, oracle, mk):
+    torch = torch_cuda
+    c = mk()
+    o = _oracle_frontend(oracle, c)
+    p = _params(lib, c)
+    S_new = torch.zeros((c.N, c.M), dtype=torch.float32, device="cuda")
+    lib.call("rn_planes_to_voxels", p, _d(torch, c.vgrid).data_ptr(), _d(torch, o["idx"]).data_ptr(),
+             _d(torch, o["cnt"]).data_ptr(), _d(torch, o["starts"]).data_ptr(), _d(torch, o["ends"]).data_ptr(),
+             _d(torch, o["S"]).data_ptr(), S_new.data_ptr(), c.N, _stream(torch))
+    assert np.abs(S_new.cpu().numpy() - o["S_vox"]).max() <= TOL_P
+    # fused front end in the reference layout (rn_mvcnn_voxel): lists bit-exact, S_vox within 1e-5
+    idx = torch.zeros((c.N, c.M, 3), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros((c.N,), dtype=torch.int32, device="cuda")
+    S_vox = torch.zeros((c.N, c.M), dtype=torch.float32, device="cuda")
+    lib.call("rn_mvcnn_voxel", p, _d(torch, c.ray_idxs).data_ptr(), _d(torch, c.features).data_ptr(),
+             _d(torch, c.P).data_ptr(), _d(torch, c.P_inv).data_ptr(), _d(torch, c.centre).data_ptr(),
+             _d(torch, c.vgrid).data_ptr(), idx.data_ptr(), cnt.data_ptr(), S_vox.data_ptr(), c.N, _stream(torch))
+    assert np.array_equal(cnt.cpu().numpy(), o["cnt"])
+    assert np.array_equal(idx.cpu().numpy(), o["idx"])
+    assert np.abs(S_vox.cpu().numpy() - o["S_vox"]).max() <= TOL_P
+
+
+# ----------------------------------------------------------------------------- a5-a8: BP
+def _random_state(c, o, seed=5):
+    """A mid-inference state: non-trivial accumulator and messages."""
+    rng = np.random.RandomState(seed)
+    acc = (PRIOR + rng.randn(*c.grid) * 2.0).astype(np.float32)
+    msgs = np.zeros((c.N, c.M), np.float32)
+    for r in range(c.N):
+        msgs[r, :o["cnt"][r]] = rng.randn(o["cnt"][r]).astype(np.float32)
+    return acc, msgs
+
+
+@pytest.mark.parametrize("mk", [case_c1, case_small])
+def test_bp_single_sweep_vs_oracle(torch_cuda, lib, oracle, mk):
+    """One synchronous sweep from identical state, reference layout (rn_bp_iteration) and
+    resident layout (rn_engine_bp_iteration): messages and sigma(acc_new) within 1e-5 of the
+    oracle in BOTH precision flavours of the reference (f32 / NumPy>=2 f64 accumulators)."""
+    torch = torch_cuda
+    c = mk()
+    o = _oracle_frontend(oracle, c)
+    acc, msgs = _random_state(c, o)
+    p = lib.make_params(M=c.M, grid_shape=c.grid)
+    d_msgs = _d(torch, msgs)
+    d_acc_out = torch.full(tuple(c.grid), PRIOR, dtype=torch.float32, device="cuda")
+    lib.call("rn_bp_iteration", p, _d(torch, o["S_vox"]).data_ptr(), _d(torch, o["idx"]).data_ptr(),
+             _d(torch, o["cnt"]).data_ptr(), _d(torch, acc).data_ptr(), d_msgs.data_ptr(), d_acc_out.data_ptr(),
+             c.N, _stream(torch))
+    g_msgs, g_acc = d_msgs.cpu().numpy(), d_acc_out.cpu().numpy()
+    for f64 in (False, True):
+        dt = np.float64 if f64 else np.float32
+        o_new = np.full(tuple(c.grid), PRIOR, dt)
+        o_msgs = msgs.copy()
+        oracle.bp_iteration(o["S_vox"], o["idx"], o["cnt"], c.grid, acc.astype(dt), o_new, o_msgs, acc_f64=f64)
+        assert np.abs(sigmoid(g_msgs) - sigmoid(o_msgs)).max() <= TOL_P
+        assert np.abs(sigmoid(g_acc) - sigmoid(o_new)).max() <= TOL_P
+        # log-odds themselves: loose absolute bound (they are not the gated quantity)
+        assert np.abs(g_msgs - o_msgs).max() < 5e-3
+    # messages beyond count and rays with count <= 1 untouched
+    for r in np.where(o["cnt"] <= 1)[0]:
+        assert np.array_equal(g_msgs[r], msgs[r])
+    # checksum property: sum(acc_new - prior) == sum of all new messages
+    valid = np.arange(c.M)[None, :] < np.where(o["cnt"] > 1, o["cnt"], 0)[:, None]
+    assert abs((g_acc.astype(np.float64) - PRIOR).sum() - g_msgs[valid].astype(np.float64).sum()) < 1e-2 * max(1, valid.sum() ** 0.5)
+
+
+@pytest.mark.parametrize("mk", [case_c1, case_small])
+def test_depth_estimate_vs_oracle(torch_cuda, lib, oracle, mk):
+    torch = torch_cuda
+    c = mk()
+    o = _oracle_frontend(oracle, c)
+    acc, msgs = _random_state(c, o, seed=9)
+    p = lib.make_params(M=c.M, grid_shape=c.grid)
+    S_new = torch.full((c.N, c.M), 3.0, dtype=torch.float32, device="cuda")
+    lib.call("rn_depth_estimate", p, _d(torch, o["S_vox"]).data_ptr(), _d(torch, o["idx"]).data_ptr(),
+             _d(torch, o["cnt"]).data_ptr(), _d(torch, acc).data_ptr(), _d(torch, msgs).data_ptr(),
+             S_new.data_ptr(), c.N, _stream(torch))
+    S_new = S_new.cpu().numpy()
+    for f64 in (False, True):
+        ref = oracle.depth_distribution(o["S_vox"], o["idx"], o["cnt"], c.grid, acc, msgs, acc_f64=f64)
+        assert np.abs(S_new - ref).max() <= TOL_P
+    occ = torch.zeros(tuple(c.grid), dtype=torch.float32, device="cuda")
+    lib.call("rn_occupancy", _d(torch, acc).data_ptr(), occ.data_ptr(), acc.size, _stream(torch))
+    assert np.abs(occ.cpu().numpy() - oracle.occupancy(acc)).max() <= 2e-7
+
+
+@pytest.mark.parametrize("iters", [1, 3])
+def test_bp_golden_fixture(torch_cuda, iters):
+    """The drop-in mrf_cuda.belief_propagation / compute_depth_distribution against outputs of
+    the reference's own mrf_np executed in the build container (tests/golden/)."""
+    import os
+    from raynet_b200.mrf import mrf_cuda
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+    S, idx, cnt, grid = g["bp_S"], g["bp_idx"], g["bp_cnt"], g["bp_grid"]
+    msgs = np.random.RandomState(0).rand(*S.shape).astype(np.float32)    # must be overwritten with 0
+    acc, msgs = mrf_cuda.belief_propagation(S, idx, cnt, msgs, grid, gamma=0.05, bp_iterations=iters,
+                                            batch_size=150)
+    assert acc.dtype == np.float32 and acc.shape == tuple(grid)
+    occ = mrf_cuda.compute_occupancy_probabilities(acc)
+    tol = TOL_P if iters == 1 else 1e-4     # f32 accumulators vs the fixture's f64 ones, amplified over sweeps
+    assert np.abs(occ - g["bp_occ_it%d" % iters]).max() <= tol
+    assert np.abs(sigmoid(msgs) - sigmoid(g["bp_msgs_it%d" % iters])).max() <= tol
+    S_new = mrf_cuda.compute_depth_distribution(S, idx, cnt, g["bp_msgs_it%d" % iters],
+                                                g["bp_acc_it%d" % iters].astype(np.float32), np.zeros_like(S),
+                                                grid, batch_size=170)
+    assert np.abs(S_new - g["bp_Snew_it%d" % iters]).max() <= TOL_P
+
+
+def test_mrf_reference_scenarios_on_gpu(torch_cuda):
+    """tests/test_mrf.py of the reference (6x6x1 grid, hand-made rays) through get_bp_backend("cuda")."""
+    from raynet_b200.common.generation_parameters import GenerationParameters
+    from raynet_b200.mrf.bp_inference import get_bp_backend
+    from raynet_b200.mrf.mrf_cuda import compute_occupancy_probabilities
+    from raynet_b200.ray_marching.ray_tracing_cuda import voxel_traversal
+    bbox = np.array([0, 0, 0, 6, 6, 1], np.float32)
+    grid = np.array([6, 6, 1], np.int32)
+    gp = GenerationParameters(grid_shape=grid, max_number_of_marched_voxels=11)
+    bp = get_bp_backend("cuda", gp, batch_size=1, bp_iterations=3)
+    M = 11
+    rays = [([0., 3.5, .5], [6., .5, .5]), ([0., 1.5, .5], [4.5, 6., .5])]
+    idx = np.zeros((2, M, 3), np.int32)
+    cnt = np.zeros((2,), np.int32)
+    for i, (s, e) in enumerate(rays):
+        cnt[i] = voxel_traversal(bbox, grid, idx[i], np.array(s, np.float32), np.array(e, np.float32))
+    S = np.zeros((2, M), np.float32)
+    S[0, 2] = S[0, 6] = 0.5
+    S[1, 4] = 1.0
+    msgs = np.random.RandomState(1).rand(2, M).astype(np.float32)
+    acc, msgs, S_new = bp.mrf_inference(S, idx, cnt, msgs, np.zeros_like(S))
+    occ = compute_occupancy_probabilities(acc).T
+    assert occ[0, 0, 2] < 0.1                                        # tests/test_mrf.py:349
+    assert S_new[0, 2] < 0.5 and S_new[0, 6] > 0.9 and S_new[1, 4] > 0.9   # :414-416
+    with pytest.raises(ValueError):
+        get_bp_backend("cuda", gp)
+
+
+# ----------------------------------------------------------------------------- fused entry points
+@pytest.mark.parametrize("mk", [case_c1, case_small])
+def test_raynet_fp_and_de_vs_oracle(torch_cuda, oracle, mk):
+    """perform_raynet_fp closures (the reference's hot kernels) against the oracle pipeline."""
+    torch = torch_cuda
+    from raynet_b200.cuda_implementations.raynet_fp import perform_raynet_fp
+    c = mk()
+    o = _oracle_frontend(oracle, c)
+    acc, msgs = _random_state(c, o, seed=11)
+    fp, de = perform_raynet_fp(c.M, c.D, c.V, 32, c.H, c.W, 11, c.bbox, c.grid, "sample_in_bbox")
+    idx = _d(torch, np.zeros((c.N, c.M, 3), np.int32))
+    cnt = _d(torch, np.zeros((c.N,), np.int32))
+    S_vox = _d(torch, np.zeros((c.N, c.M), np.float32))
+    acc_out = _d(torch, np.full(tuple(c.grid), PRIOR, np.float32))
+    d_msgs = _d(torch, msgs)
+    ret = fp(c.ray_idxs, c.features.ravel(), c.P.ravel(), c.P_inv.ravel(), c.centre, c.vgrid.ravel(), idx, cnt,
+             S_vox, acc, d_msgs, acc_out)
+    g_msgs = ret.get()
+    assert np.array_equal(cnt.cpu().numpy(), o["cnt"]) and np.array_equal(idx.cpu().numpy(), o["idx"])
+    assert np.abs(S_vox.cpu().numpy() - o["S_vox"]).max() <= TOL_P
+    o_new = np.full(tuple(c.grid), PRIOR, np.float32)
+    o_msgs = msgs.copy()
+    oracle.bp_iteration(o["S_vox"], o["idx"], o["cnt"], c.grid, acc, o_new, o_msgs)
+    assert np.abs(sigmoid(g_msgs) - sigmoid(o_msgs)).max() <= TOL_P
+    assert np.abs(sigmoid(acc_out.cpu().numpy()) - sigmoid(o_new)).max() <= TOL_P
+    # depth estimation closure
+    depth = _d(torch, np.zeros((c.N,), np.float32))
+    de(c.ray_idxs, c.features.ravel(), c.P.ravel(), c.P_inv.ravel(), c.centre, c.vgrid.ravel(), idx, cnt, S_vox,
+       acc, msgs, depth)
+    ref_Snew = oracle.depth_distribution(o["S_vox"], o["idx"], o["cnt"], c.grid, acc, msgs)
+    assert np.abs(S_vox.cpu().numpy() - ref_Snew).max() <= TOL_P
+    ref_depth, ref_am = oracle.argmax_depth(ref_Snew, o["idx"], c.vgrid, c.grid, c.centre)
+    _assert_depth_matches(depth.cpu().numpy(), ref_depth, ref_Snew)
+    with pytest.raises(AssertionError):
+        fp(c.ray_idxs, c.features.ravel(), c.P.ravel(), c.P_inv.ravel(), c.centre, c.vgrid.ravel(), idx, cnt,
+           S_vox[:, :-1], acc, d_msgs, acc_out)
+
+
+def _assert_depth_matches(depth, ref_depth, ref_Snew, gap=1e-5):
+    """Depth is the distance to the arg-max voxel: exact wherever the top-2 gap of the
+    distribution exceeds the 1e-5 parity tolerance."""
+    top2 = -np.sort(-ref_Snew, axis=1)[:, :2]
+    decided = (top2[:, 0] - top2[:, 1]) > gap
+    assert decided.mean() > 0.9
+    assert np.abs(depth[decided] - ref_depth[decided]).max() < 1e-6
+    assert (np.abs(depth - ref_depth) < 1e-6).mean() > 0.995
+
+
+# ----------------------------------------------------------------------------- resident engine, end to end
+def _run_engine(torch, c, iters, refs=None):
+    from raynet_b200.engine import RayPotentialEngine
+    refs = refs if refs is not None else [c.ref_idx]
+    eng = RayPotentialEngine(c.M, c.D, c.V, 32, c.H, c.W, 11, c.bbox, c.grid, max_rays=c.N * len(refs),
+                             use_distributed=False)
+    eng.set_voxel_grid(c.vgrid)
+    feats = _d(torch, c.features_all)
+    for ref in refs:
+        c.set_reference(ref, c.N if c.N < c.H * c.W else None)
+        eng.add_image(_d(torch, c.ray_idxs), feats, _d(torch, c.P), _d(torch, c.P_inv), _d(torch, c.centre),
+                      view_ids=_d(torch, c.view_ids))
+    eng.finalize_frontend()
+    eng.run_bp(iters)
+    return eng
+
+
+@pytest.mark.parametrize("mk,iters", [(case_c1, 3), (case_small, 3)])
+def test_engine_end_to_end_vs_oracle(torch_cuda, oracle, mk, iters):
+    """C1 (and a longer-ray case) through the resident pipeline: every view a reference view in
+    turn, I sweeps, depth pass -- against the oracle run the same way."""
+    torch = torch_cuda
+    c = mk()
+    refs = list(range(c.V))
+    eng = _run_engine(torch, c, iters, refs)
+    # oracle: concatenate the per-image front ends, then mrf_np-style BP
+    fronts = []
+    for ref in refs:
+        c.set_reference(ref, c.N)
+        fronts.append((_oracle_frontend(oracle, c), c.centre.copy()))
+    idx = np.concatenate([f["idx"] for f, _ in fronts])
+    cnt = np.concatenate([f["cnt"] for f, _ in fronts])
+    S_vox = np.concatenate([f["S_vox"] for f, _ in fronts])
+    assert np.array_equal(eng.count.cpu().numpy(), cnt)
+    assert np.array_equal(eng.voxel_indices().cpu().numpy(), idx)
+    g_occ = eng.occupancy().cpu().numpy()
+    worst = {}
+    for f64 in (False, True):
+        acc, msgs = oracle.belief_propagation(S_vox, idx, cnt, c.grid, gamma=0.05, bp_iterations=iters, acc_f64=f64)
+        worst[f64] = np.abs(g_occ - oracle.occupancy(acc)).max()
+    # multi-sweep gate: the reference's own two precision flavours differ by ~2e-5 here, so the
+    # kernel must be within 1e-5 of at least one flavour and within 5e-5 of both
+    assert min(worst.values()) <= TOL_P, worst
+    assert max(worst.values()) <= 5e-5, worst
+    # depth pass from the engine's own final state vs oracle on that same state
+    g_acc = eng.acc_prev.cpu().numpy()
+    g_msgs = eng.msgs[:eng.n_rays].cpu().numpy()
+    ref_Snew = oracle.depth_distribution(S_vox, idx, cnt, c.grid, g_acc, g_msgs)
+    depth = eng.depth().cpu().numpy()
+    n0 = 0
+    for f, centre in fronts:
+        n = f["cnt"].shape[0]
+        ref_depth, _ = oracle.argmax_depth(ref_Snew[n0:n0 + n], f["idx"], c.vgrid, c.grid, centre)
+        _assert_depth_matches(depth[n0:n0 + n], ref_depth, ref_Snew[n0:n0 + n])
+        n0 += n
+
+
+def test_engine_equals_reference_layout_path(torch_cuda, lib, oracle):
+    """Size-independent property used at full size too: the resident pipeline and the
+    reference-layout entry points are the same arithmetic (identical messages)."""
+    torch = torch_cuda
+    c = case_small()
+    eng = _run_engine(torch, c, 0)
+    o = _oracle_frontend(oracle, c)
+    p = lib.make_params(M=c.M, grid_shape=c.grid)
+    acc, msgs = _random_state(c, o, seed=2)
+    eng.msgs[:c.N].copy_(_d(torch, msgs))
+    eng.acc_prev.copy_(_d(torch, acc))
+    eng.bp_iteration()
+    S_vox = torch.zeros((c.N, c.M), dtype=torch.float32, device="cuda")
+    idx = torch.zeros((c.N, c.M, 3), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros((c.N,), dtype=torch.int32, device="cuda")
+    pf = _params(lib, c)
+    lib.call("rn_mvcnn_voxel", pf, _d(torch, c.ray_idxs).data_ptr(), _d(torch, c.features).data_ptr(),
+             _d(torch, c.P).data_ptr(), _d(torch, c.P_inv).data_ptr(), _d(torch, c.centre).data_ptr(),
+             _d(torch, c.vgrid).data_ptr(), idx.data_ptr(), cnt.data_ptr(), S_vox.data_ptr(), c.N, _stream(torch))
+    d_msgs = _d(torch, msgs)
+    acc_out = torch.full(tuple(c.grid), PRIOR, dtype=torch.float32, device="cuda")
+    lib.call("rn_bp_iteration", p, S_vox.data_ptr(), idx.data_ptr(), cnt.data_ptr(), _d(torch, acc).data_ptr(),
+             d_msgs.data_ptr(), acc_out.data_ptr(), c.N, _stream(torch))
+    a, b = eng.msgs[:c.N].cpu().numpy(), d_msgs.cpu().numpy()
+    assert np.abs(sigmoid(a) - sigmoid(b)).max() <= 2e-6
+    assert np.abs(sigmoid(eng.acc_prev.cpu().numpy()) - sigmoid(acc_out.cpu().numpy())).max() <= 2e-6
+
+
+def test_empty_and_degenerate_batches(torch_cuda, lib):
+    """n_rays == 0 is a no-op for every entry point; rays with count 0 / 1 leave the
+    accumulator at the prior."""
+    torch = torch_cuda
+    c = case_c1()
+    p = _params(lib, c)
+    z = torch.zeros((4,), dtype=torch.float32, device="cuda")
+    zi = torch.zeros((4,), dtype=torch.int32, device="cuda")
+    lib.call("rn_voxel_traversal", p, z.data_ptr(), z.data_ptr(), zi.data_ptr(), zi.data_ptr(), 0, _stream(torch))
+    lib.call("rn_bp_iteration", p, z.data_ptr(), zi.data_ptr(), zi.data_ptr(), z.data_ptr(), z.data_ptr(),
+             z.data_ptr(), 0, _stream(torch))
+    lib.call("rn_occupancy", z.data_ptr(), z.data_ptr(), 0, _stream(torch))
+    # two rays: one misses (count 0), one clips a corner voxel only (count 1)
+    bbox = np.array([0, 0, 0, 4, 4, 4], np.float32)
+    grid = np.array([4, 4, 4], np.int32)
+    pp = lib.make_params(M=8, bbox=bbox, grid_shape=grid)
+    starts = _d(torch, np.array([[9, 9, 9], [0.5, 0.5, 0.5]], np.float32))
+    ends = _d(torch, np.array([[10, 10, 10], [0.6, 0.6, 0.6]], np.float32))
+    idx = torch.zeros((2, 8, 3), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros((2,), dtype=torch.int32, device="cuda")
+    lib.call("rn_voxel_traversal", pp, starts.data_ptr(), ends.data_ptr(), idx.data_ptr(), cnt.data_ptr(), 2,
+             _stream(torch))
+    assert cnt.cpu().tolist() == [0, 1]
+    S = torch.full((2, 8), 0.125, dtype=torch.float32, device="cuda")
+    msgs = torch.zeros((2, 8), dtype=torch.float32, device="cuda")
+    acc = torch.full((4, 4, 4), PRIOR, dtype=torch.float32, device="cuda")
+    acc_out = acc.clone()
+    lib.call("rn_bp_iteration", pp, S.data_ptr(), idx.data_ptr(), cnt.data_ptr(), acc.data_ptr(), msgs.data_ptr(),
+             acc_out.data_ptr(), 2, _stream(torch))
+    assert torch.equal(acc_out, acc) and float(msgs.abs().max()) == 0.0
+    S_new = torch.ones((2, 8), dtype=torch.float32, device="cuda")
+    lib.call("rn_depth_estimate", pp, S.data_ptr(), idx.data_ptr(), cnt.data_ptr(), acc.data_ptr(), msgs.data_ptr(),
+             S_new.data_ptr(), 2, _stream(torch))
+    assert float(S_new.abs().max()) == 0.0
+
+
+def test_error_mapping(torch_cuda, lib):
+    """RN_ERR_SHAPE -> AssertionError, RN_ERR_UNSUPPORTED -> NotImplementedError."""
+    torch = torch_cuda
+    z = torch.zeros((4,), dtype=torch.float32, device="cuda")
+    with pytest.raises(AssertionError):
+        lib.call("rn_voxel_traversal", lib.make_params(M=8, bbox=[0, 0, 0, 1, 1, 1], grid_shape=[0, 4, 4]),
+                 z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, _stream(torch))
+    with pytest.raises(NotImplementedError):
+        lib.call("rn_voxel_traversal", lib.make_params(M=8, bbox=[0, 0, 0, 1, 1, 1], grid_shape=[2048, 4, 4]),
+                 z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, _stream(torch))
+    from raynet_b200.cuda_implementations.raynet_fp import perform_raynet_fp
+    with pytest.raises(NotImplementedError):
+        perform_raynet_fp(8, 4, 2, 32, 8, 8, 11, [0, 0, 0, 1, 1, 1], [4, 4, 4], "sample_in_range")
+
+
+def test_forward_pass_factory_runs(torch_cuda, oracle):
+    """scripts/forward_pass.py's usage: factory -> generator of (H, W) depth maps, for the
+    three factories; the raynet one is checked against the oracle run the same way."""
+    from raynet_b200.common.generation_parameters import GenerationParameters
+    from raynet_b200.forward_pass import get_forward_pass_factory
+    from raynet_b200.synth import SyntheticScene, random_features
+    V, H, W, G, D, M = 3, 24, 20, 24, 8, 72
+    scene = SyntheticScene(V, H, W, (G, G, G), with_images=True)
+    feats = random_features(V, H, W, 32, 11, seed=4)
+
+    class Model(object):
+        """stands for the Keras MV-CNN: returns the feature maps of the views it is given"""
+        def __init__(self):
+            self.order = None
+
+        def predict(self, x):
+            return feats[self.order]
+
+    gp = GenerationParameters(depth_planes=D, neighbors=V - 1, grid_shape=np.array([G, G, G], np.int32),
+                              max_number_of_marched_voxels=M, padding=11, gamma_mrf=0.05)
+    outs = {}
+    for name in ("multi_view_cnn", "multi_view_cnn_voxel_space", "raynet"):
+        model = Model()
+        fp = get_forward_pass_factory(name)(model, gp, "sample_in_bbox", scene.image_shape, 200)
+        orig = scene.get_image_with_neighbors
+
+        def hooked(i, model=model, orig=orig):
+            model.order = scene.view_order(i)
+            return orig(i)
+        scene.get_image_with_neighbors = hooked
+        maps = list(fp.forward_pass(scene, (0, V, 1)))
+        scene.get_image_with_neighbors = orig
+        assert len(maps) == V and all(m.shape == (H, W) and m.dtype == np.float32 for m in maps)
+        assert all(np.isfinite(m).all() and (m > 0).all() for m in maps)
+        outs[name] = maps
+    with pytest.raises(KeyError):
+        get_forward_pass_factory("nope")

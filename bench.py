@@ -219,6 +219,42 @@ def run_reference_arm(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def run_e2e(args, cfg, scene, model, my_images, rank, world, dev, barrier, total_rays):
+    """e2e arm: reference-facing plug-in call, host buffers in and out."""
+    import torch
+    import torch.distributed as dist
+    from raynet_b200.common.generation_parameters import GenerationParameters
+    from raynet_b200.forward_pass import RayNetForwardPass
+    H, W, G, V, D, M, I = (cfg[k] for k in ("H", "W", "G", "V", "D", "M", "I"))
+    n_total = scene.n_images
+    gp = GenerationParameters(depth_planes=D, neighbors=V - 1, grid_shape=np.array([G, G, G], np.int32),
+                              max_number_of_marched_voxels=M, padding=PADDING, gamma_mrf=GAMMA)
+    fp = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, rays_batch=H * W, bp_iterations=I)
+    images_range = (rank, n_total, world)
+
+    def e2e_step():
+        maps = list(fp.forward_pass(scene, images_range))
+        assert len(maps) == len(my_images) and maps[0].shape == (H, W)
+        return maps
+
+    for _ in range(2):
+        e2e_step()
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    return {"value": total_rays / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
+            "h2d_bytes_per_step": int(fp.h2d_bytes), "d2h_bytes_per_step": int(fp.d2h_bytes),
+            "api": "raynet_b200.forward_pass.RayNetForwardPass.forward_pass(scene, images_range), pinned host "
+                   "feature maps in, host depth maps out; host wall clock around the call"}
+
+
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
@@ -324,35 +360,10 @@ def run_gpu_arm(args, cfg):
     total_rays = n_rays * world
     value = total_rays / (ms_step * 1e-3)
 
-    # ---------------- e2e arm: reference-facing plug-in call, host buffers --------------------------
-    gp = GenerationParameters(depth_planes=D, neighbors=V - 1, grid_shape=np.array([G, G, G], np.int32),
-                              max_number_of_marched_voxels=M, padding=PADDING, gamma_mrf=GAMMA)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, cfg, scene, model, my_images, rank, world, dev, barrier, total_rays)
     del eng, feats
-    torch.cuda.empty_cache()
-    fp = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, rays_batch=H * W, bp_iterations=I)
-    images_range = (rank, n_total, world)
-
-    def e2e_step():
-        maps = list(fp.forward_pass(scene, images_range))
-        assert len(maps) == len(my_images) and maps[0].shape == (H, W)
-        return maps
-
-    for _ in range(2):
-        e2e_step()
-    e2e_steps = max(2, min(args.steps, 5))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms.item())
-    e2e = {"value": total_rays / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(fp.h2d_bytes), "d2h_bytes_per_step": int(fp.d2h_bytes),
-           "api": "raynet_b200.forward_pass.RayNetForwardPass.forward_pass(scene, images_range), pinned host "
-                  "feature maps in, host depth maps out; host wall clock around the call"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -414,6 +425,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs only)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RN_ABI_VERSION 1
+#define RN_ABI_VERSION 2
 
 typedef enum RnStatus {
     RN_OK = 0,
@@ -163,15 +163,27 @@ int rn_mvcnn_voxel_depth(const RnParams *p, const int32_t *ray_idxs, const float
  * loop of RayNetForwardPass.forward_pass, forward_pass.py:593-748, which re-runs the
  * front end and bounces messages through host memory on every sweep).
  *
- * Per-ray state kept in HBM between sweeps:
+ * Per-ray state kept in HBM between sweeps (max_voxels <= 1024; R = rn_row_stride(max_voxels)):
  *   ray_hdr   uint32 [n][2]  first voxel + step signs      (8 B / ray)
- *   codes     uint8  [n][code_stride]  2-bit axis code per traversed voxel (0.25 B / voxel)
+ *   codes     uint8  [n][code_stride]  2 bits per traversed voxel, stored as one (lo, hi) pair
+ *             of 32-bit bit planes per 32 voxels; code = the axis stepped along to ENTER the
+ *             voxel, 3 = none (0.25 B / voxel).  rn_code_stride(M) = bytes per ray.
  *   count     int32  [n]
- *   s_hat     float32 [n][M]  clip_and_renorm(S_voxel_space[r, :count])  (mrf_np.py:4-8)
- *   msgs      float32 [n][M]
- * rn_code_stride(M) gives the byte stride of one ray's code row.
+ *   s_hat     float32 [n][R]  clip_and_renorm(S_voxel_space[r, :count])  (mrf_np.py:4-8)
+ *   msgs      float32 [n][R]
+ * The two occupancy accumulators of the resident pipeline are BRICKED (4x4x2-voxel 128-byte
+ * lines of four 2x2x2-voxel sectors; rn_brick_elems floats, padding included); convert with
+ * rn_grid_to_bricks / rn_bricks_to_grid.
  * ------------------------------------------------------------------------------------- */
 int64_t rn_code_stride(int32_t max_voxels);
+int64_t rn_row_stride(int32_t max_voxels);      /* floats per ray of s_hat / msgs rows: M rounded up to 128 */
+int rn_num_classes(void);                       /* number of ray-length classes (see rn_engine_bin_rays) */
+int64_t rn_brick_elems(const RnParams *p);      /* floats of a bricked accumulator for p->grid (-1 on error) */
+
+/* row-major float32 [Gx][Gy][Gz] -> bricked (padding voxels := pad) and back; the way back
+ * optionally applies compute_occupancy_probabilities (mrf_np.py:206-240). */
+int rn_grid_to_bricks(const RnParams *p, const float *grid, float *bricks, float pad, void *stream);
+int rn_bricks_to_grid(const RnParams *p, const float *bricks, float *grid, int apply_sigmoid, void *stream);
 
 /* Front end once per reference image: fills starts/ends (may be NULL), ray_hdr, codes,
  * count, s_hat.  axis_centres: float32 [Gx+Gy+Gz] voxel-centre coordinates per axis
@@ -186,17 +198,34 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
                        float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *s_hat,
                        int64_t n_rays, void *stream);
 
-/* One BP sweep over resident state; msgs updated in place, acc_out += messages.
- * max_count: upper bound on count[] for this launch (<= max_voxels; pass max_voxels if
- * unknown) -- selects the register-resident ray length of the kernel. */
+/* Group the rays by length class (class c = ceil(count / 128) for count >= 2, class 0 = the rays
+ * BP skips) so that each class runs with the shared memory its rays need.  order: int32 [n]
+ * out, the ray positions class by class; inside a class rays follow an 8x8-pixel tiled
+ * enumeration of each image when seg_len (= rays per reference image, column-major ids as the
+ * reference enumerates them, p->height pixels per column) allows it, else ray order.
+ * class_scratch: uint64 [2 * rn_num_classes()] device scratch; on return its first
+ * rn_num_classes() entries hold the class sizes (the caller prefix-sums them into the
+ * class_offsets of rn_engine_bp_iteration). */
+int rn_engine_bin_rays(const RnParams *p, const int32_t *count, int64_t n_rays, int64_t seg_len, int32_t *order,
+                       uint64_t *class_scratch, void *stream);
+
+/* One BP sweep over resident state; msgs updated in place, acc_out += messages (bricked grids).
+ * order / class_offsets (HOST int64 [rn_num_classes() + 1], may both be NULL): the binning of
+ * rn_engine_bin_rays.  first_sweep != 0: messages are taken as all-zero and not read
+ * (mrf_np.py:275).  max_count: upper bound on count[] (used when there is no binning). */
 int rn_engine_bp_iteration(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes,
                            const int32_t *count, const float *s_hat, float *msgs, const float *acc_in,
-                           float *acc_out, int32_t max_count, int64_t n_rays, void *stream);
+                           float *acc_out, const int32_t *order, const int64_t *class_offsets,
+                           int32_t first_sweep, int32_t max_count, int64_t n_rays, void *stream);
 
-/* Depth pass over resident state: depth_map[r] = |centre(voxel argmax_i o_i cp_i s_i) - C|. */
+/* Depth pass over resident state, all reference images in one launch:
+ * depth_map[r] = |centre(voxel argmax_i o_i cp_i s_i) - C_image(r)|.  centres: float32 [n_seg][4];
+ * seg_starts: device int64 [n_seg + 1], first ray of every image (ignored when n_seg == 1).
+ * S_new (may be NULL): float32 [n][R], the normalised depth distribution (parity tests). */
 int rn_engine_depth(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count,
                     const float *s_hat, const float *msgs, const float *acc, const float *axis_centres,
-                    const float *centre, float *depth_map, int32_t max_count, int64_t n_rays, void *stream);
+                    const float *centres, const int64_t *seg_starts, int32_t n_seg, float *depth_map,
+                    float *S_new, int64_t n_rays, void *stream);
 
 /* Expand resident state into the reference's dense buffers (parity tests / debugging):
  * ray_voxel_indices int32 [n][M][3] (zero beyond count). */

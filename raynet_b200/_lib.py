@@ -68,14 +68,18 @@ SIGNATURES = {
     "rn_mvcnn_voxel": [_PP] + [_PTR] * 9 + [_I64, _PTR],
     "rn_mvcnn_voxel_depth": [_PP] + [_PTR] * 10 + [_I64, _PTR],
     "rn_engine_frontend": [_PP, _PTR, _PTR, _PTR, _I32] + [_PTR] * 10 + [_I64, _PTR],
-    "rn_engine_bp_iteration": [_PP] + [_PTR] * 7 + [_I32, _I64, _PTR],
-    "rn_engine_depth": [_PP] + [_PTR] * 9 + [_I32, _I64, _PTR],
+    "rn_engine_bin_rays": [_PP, _PTR, _I64, _I64, _PTR, _PTR, _PTR],
+    "rn_engine_bp_iteration": [_PP] + [_PTR] * 9 + [_I32, _I32, _I64, _PTR],
+    "rn_engine_depth": [_PP] + [_PTR] * 9 + [_I32, _PTR, _PTR, _I64, _PTR],
+    "rn_grid_to_bricks": [_PP, _PTR, _PTR, ctypes.c_float, _PTR],
+    "rn_bricks_to_grid": [_PP, _PTR, _PTR, _I32, _PTR],
     "rn_engine_expand_indices": [_PP, _PTR, _PTR, _PTR, _PTR, _I64, _PTR],
     "rn_axis_centres": [_PP, _PTR, _PTR, _PTR],
     "rn_add_prior": [_PTR, ctypes.c_float, _I64, _PTR],
     "rn_max_count": [_PTR, _I64, _PTR, _PTR],
 }
-OTHER_SYMBOLS = ["rn_last_error", "rn_abi_version", "rn_device_info", "rn_code_stride"]
+OTHER_SYMBOLS = ["rn_last_error", "rn_abi_version", "rn_device_info", "rn_code_stride", "rn_row_stride", "rn_num_classes",
+                 "rn_brick_elems"]
 
 _lib = None
 
@@ -105,6 +109,12 @@ def load():
     lib.rn_code_stride.argtypes = [ctypes.c_int32]
     lib.rn_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3
     lib.rn_device_info.restype = ctypes.c_int
+    lib.rn_row_stride.restype = ctypes.c_int64
+    lib.rn_row_stride.argtypes = [ctypes.c_int32]
+    lib.rn_num_classes.restype = ctypes.c_int
+    lib.rn_num_classes.argtypes = []
+    lib.rn_brick_elems.restype = ctypes.c_int64
+    lib.rn_brick_elems.argtypes = [_PP]
     _lib = lib
     return lib
 
@@ -127,3 +137,18 @@ def call(name, *args):
 
 def code_stride(M):
     return int(load().rn_code_stride(int(M)))
+
+
+def row_stride(M):
+    return int(load().rn_row_stride(int(M)))
+
+
+def num_classes():
+    return int(load().rn_num_classes())
+
+
+def brick_elems(params):
+    n = int(load().rn_brick_elems(ctypes.byref(params)))
+    if n < 0:
+        check(RN_ERR_SHAPE)
+    return n

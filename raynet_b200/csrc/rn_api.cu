@@ -24,10 +24,11 @@ int check_launch(const char *what) {
     return RN_OK;
 }
 
-inline int64_t code_stride_of(int M) {
-    int64_t b = (M + 3) / 4;
-    return (b + 31) / 32 * 32;
+inline int64_t code_stride_of(int M) {   // 2 bits per voxel, whole 128-voxel chunks (32 bytes each)
+    return (int64_t)((M + RN_CHUNK - 1) / RN_CHUNK) * 32;
 }
+
+inline int64_t row_stride_of(int M) { return (int64_t)((M + RN_CHUNK - 1) / RN_CHUNK) * RN_CHUNK; }
 
 // Derived parameters.  bin = (max - min) / grid in float32, exactly ray_tracing.pyx:103-104.
 int make_dev(const RnParams *p, RnDev &d, bool need_grid, bool need_views, bool resident) {
@@ -48,6 +49,12 @@ int make_dev(const RnParams *p, RnDev &d, bool need_grid, bool need_views, bool 
             volatile float b = ext / (float)p->grid[a];
             d.bin[a] = b;
         }
+        d.bbx = (d.gx + 3) / 4;
+        d.bby = (d.gy + 3) / 4;
+        d.blz = (d.gz + 1) / 2;
+        d.bsy = d.blz * 32;
+        d.bsx = d.bby * d.bsy;
+        if ((int64_t)d.bbx * d.bsx >= (1ll << 31)) return fail(RN_ERR_UNSUPPORTED, "grid too large for int32 indices");
     }
     if (need_views) {
         if (d.D < 2 || d.D > 128) return fail(RN_ERR_UNSUPPORTED, "depth_planes must be in [2, 128]");
@@ -63,8 +70,11 @@ int make_dev(const RnParams *p, RnDev &d, bool need_grid, bool need_views, bool 
     }
     d.code_stride = (int)code_stride_of(d.M);
     d.row_stride = d.M;
-    if (resident && (d.M % 4) != 0)
-        return fail(RN_ERR_SHAPE, "resident layout needs max_voxels to be a multiple of 4 (rows are 128-bit accessed)");
+    if (resident) {   // rows padded to whole 128-voxel chunks (16-byte aligned for the TMA bulk copies)
+        if (d.M > RN_MAX_NCH * RN_CHUNK)
+            return fail(RN_ERR_UNSUPPORTED, "resident layout supports at most %d voxels per ray", RN_MAX_NCH * RN_CHUNK);
+        d.row_stride = (int)row_stride_of(d.M);
+    }
     return RN_OK;
 }
 
@@ -90,13 +100,20 @@ inline int nch_for(int max_count) {
         default: return fail(RN_ERR_UNSUPPORTED, "rays longer than %d voxels are not supported", RN_MAX_NCH * RN_CHUNK); \
     }
 
-template <bool kCodes>
 int launch_dda(const RnDev &d, const DdaArgs &a, cudaStream_t st) {
     if (a.n_rays <= 0) return RN_OK;
     const int threads = 128;
     const int64_t blocks = (a.n_rays + threads - 1) / threads;
-    dda_kernel<kCodes><<<(unsigned)blocks, threads, 0, st>>>(d, a);
+    dda_kernel<<<(unsigned)blocks, threads, 0, st>>>(d, a);
     return check_launch("dda_kernel");
+}
+
+int launch_dda_codes(const RnDev &d, const DdaCodesArgs &a, cudaStream_t st) {
+    if (a.n_rays <= 0) return RN_OK;
+    const int threads = 128;
+    const int64_t blocks = (a.n_rays + threads - 1) / threads;
+    dda_codes_kernel<<<(unsigned)blocks, threads, 0, st>>>(d, a);
+    return check_launch("dda_codes_kernel");
 }
 
 template <int NCH, bool kAos>
@@ -123,24 +140,33 @@ int launch_simmap(const RnDev &d, const SimMapArgs &a, int max_count, bool mappi
     return RN_OK;
 }
 
-template <bool kEngine>
-int launch_bp(const RnDev &d, const BpArgs &a, int max_count, cudaStream_t st) {
-    if (a.n_rays <= 0) return RN_OK;
-    const int threads = 256;
-    const int64_t blocks = (a.n_rays * 32 + threads - 1) / threads;
-    int nch = nch_for(max_count);
-    RN_DISPATCH_NCH(nch, (bp_kernel<NCH, kEngine><<<(unsigned)blocks, threads, 0, st>>>(d, a)));
-    return check_launch("bp_kernel");
+// One BP sweep over rays [a.first, a.first + a.n) of a.order (or of the ray array itself).
+template <bool kAos>
+int launch_bp2(const RnDev &d, Bp2Args a, bool first_sweep, int nch_max, cudaStream_t st) {
+    if (a.n <= 0) return RN_OK;
+    if (nch_max < 1 || nch_max > RN_MAX_NCH)
+        return fail(RN_ERR_UNSUPPORTED, "rays longer than %d voxels are not supported", RN_MAX_NCH * RN_CHUNK);
+    static thread_local bool configured = false;
+    if (!configured) {   // the largest class needs more than the 48 KB default
+        const int mx = (int)(4 * rn_bp2_warp_bytes(RN_MAX_NCH));
+        cudaError_t e = cudaFuncSetAttribute(bp2_kernel<true, kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bp2_kernel<false, kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "bp2 smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    a.nch_max = nch_max;
+    const size_t smem = 4 * rn_bp2_warp_bytes(nch_max);
+    const unsigned blocks = (unsigned)((a.n + 3) / 4);
+    if (first_sweep) bp2_kernel<true, kAos><<<blocks, 128, smem, st>>>(d, a);
+    else bp2_kernel<false, kAos><<<blocks, 128, smem, st>>>(d, a);
+    return check_launch("bp2_kernel");
 }
 
-template <bool kEngine>
-int launch_depth(const RnDev &d, const DepthArgs &a, int max_count, cudaStream_t st) {
+template <bool kAos>
+int launch_depth2(const RnDev &d, const Depth2Args &a, cudaStream_t st) {
     if (a.n_rays <= 0) return RN_OK;
-    const int threads = 256;
-    const int64_t blocks = (a.n_rays * 32 + threads - 1) / threads;
-    int nch = nch_for(max_count);
-    RN_DISPATCH_NCH(nch, (depth_kernel<NCH, kEngine><<<(unsigned)blocks, threads, 0, st>>>(d, a)));
-    return check_launch("depth_kernel");
+    depth2_kernel<kAos><<<(unsigned)((a.n_rays + 3) / 4), 128, 0, st>>>(d, a);
+    return check_launch("depth2_kernel");
 }
 
 inline unsigned grid_for(int64_t n, int threads, int64_t cap = 148 * 16) {
@@ -192,6 +218,7 @@ int rn_device_info(int *sm_count, int *cc_major, int *cc_minor) {
 }
 
 int64_t rn_code_stride(int32_t max_voxels) { return code_stride_of(max_voxels); }
+int64_t rn_row_stride(int32_t max_voxels) { return row_stride_of(max_voxels); }
 
 int rn_sample_in_bbox(const RnParams *p, const int32_t *ray_idxs, const float *P_inv, const float *centre,
                       float *starts, float *ends, int64_t n_rays, void *stream) {
@@ -256,7 +283,7 @@ int rn_voxel_traversal(const RnParams *p, const float *starts, const float *ends
     DdaArgs a = {};
     a.starts = const_cast<float *>(starts); a.ends = const_cast<float *>(ends);
     a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.n_rays = n_rays;
-    return launch_dda<false>(d, a, S(stream));
+    return launch_dda(d, a, S(stream));
 }
 
 int rn_axis_centres(const RnParams *p, const float *voxel_grid, float *axis_centres, void *stream) {
@@ -292,10 +319,10 @@ int rn_bp_iteration(const RnParams *p, const float *S_in, const int32_t *ray_vox
     RnDev d;
     int rc = make_dev(p, d, true, false, false);
     if (rc) return rc;
-    BpArgs a = {};
-    a.S = S_in; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc_in = acc_in; a.msgs = msgs;
-    a.acc_out = acc_out; a.n_rays = n_rays;
-    return launch_bp<false>(d, a, d.M, S(stream));
+    Bp2Args a = {};
+    a.s_hat = S_in; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc_in = acc_in; a.msgs = msgs;
+    a.acc_out = acc_out; a.first = 0; a.n = n_rays;
+    return launch_bp2<true>(d, a, false, (d.M + RN_CHUNK - 1) / RN_CHUNK, S(stream));
 }
 
 int rn_depth_estimate(const RnParams *p, const float *S_in, const int32_t *ray_voxel_indices,
@@ -304,10 +331,10 @@ int rn_depth_estimate(const RnParams *p, const float *S_in, const int32_t *ray_v
     RnDev d;
     int rc = make_dev(p, d, true, false, false);
     if (rc) return rc;
-    DepthArgs a = {};
-    a.S = S_in; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc = acc; a.msgs = msgs;
+    Depth2Args a = {};
+    a.s_hat = S_in; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc = acc; a.msgs = msgs;
     a.S_new = S_new; a.n_rays = n_rays;
-    return launch_depth<false>(d, a, d.M, S(stream));
+    return launch_depth2<true>(d, a, S(stream));
 }
 
 int rn_occupancy(const float *acc, float *out, int64_t n, void *stream) {
@@ -344,7 +371,7 @@ static int frontend_ref_layout(const RnDev &d, const int32_t *ray_idxs, const fl
     DdaArgs da = {};
     da.ray_idxs = ray_idxs; da.P_inv = P_inv; da.centre = centre;
     da.idx = ray_voxel_indices; da.count = ray_voxel_count; da.n_rays = n_rays;
-    int rc = launch_dda<false>(d, da, st);
+    int rc = launch_dda(d, da, st);
     if (rc) return rc;
     SimMapArgs a = {};
     a.ray_idxs = ray_idxs; a.features = features; a.P = P; a.P_inv = P_inv; a.centre = centre;
@@ -367,10 +394,10 @@ int rn_raynet_fp(const RnParams *p, const int32_t *ray_idxs, const float *featur
     rc = frontend_ref_layout(d, ray_idxs, features, P, P_inv, centre, axes, ray_voxel_indices, ray_voxel_count,
                              S_voxel_space, nullptr, n_rays, S(stream));
     if (rc) return rc;
-    BpArgs a = {};
-    a.S = S_voxel_space; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc_in = acc_in; a.msgs = msgs;
-    a.acc_out = acc_out; a.n_rays = n_rays;
-    return launch_bp<false>(d, a, d.M, S(stream));
+    Bp2Args a = {};
+    a.s_hat = S_voxel_space; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc_in = acc_in; a.msgs = msgs;
+    a.acc_out = acc_out; a.first = 0; a.n = n_rays;
+    return launch_bp2<true>(d, a, false, (d.M + RN_CHUNK - 1) / RN_CHUNK, S(stream));
 }
 
 int rn_raynet_de(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
@@ -387,10 +414,10 @@ int rn_raynet_de(const RnParams *p, const int32_t *ray_idxs, const float *featur
     rc = frontend_ref_layout(d, ray_idxs, features, P, P_inv, centre, axes, ray_voxel_indices, ray_voxel_count,
                              S_voxel_space, nullptr, n_rays, S(stream));
     if (rc) return rc;
-    DepthArgs a = {};
-    a.S = S_voxel_space; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc = acc; a.msgs = msgs;
-    a.axes = axes; a.centre = centre; a.S_new = S_voxel_space; a.depth_map = depth_map; a.n_rays = n_rays;
-    return launch_depth<false>(d, a, d.M, S(stream));
+    Depth2Args a = {};
+    a.s_hat = S_voxel_space; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc = acc; a.msgs = msgs;
+    a.axes = axes; a.centres = centre; a.n_seg = 1; a.S_new = S_voxel_space; a.depth_map = depth_map; a.n_rays = n_rays;
+    return launch_depth2<true>(d, a, S(stream));
 }
 
 int rn_mvcnn_voxel(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
@@ -424,6 +451,32 @@ int rn_mvcnn_voxel_depth(const RnParams *p, const int32_t *ray_idxs, const float
 }
 
 // ---- resident pipeline ------------------------------------------------------------------
+int rn_num_classes(void) { return RN_NCLASS; }
+
+int64_t rn_brick_elems(const RnParams *p) {
+    RnDev d;
+    if (make_dev(p, d, true, false, false)) return -1;
+    return (int64_t)d.bbx * d.bsx;
+}
+
+int rn_grid_to_bricks(const RnParams *p, const float *grid, float *bricks, float pad, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    const int64_t nb = (int64_t)d.bbx * d.bsx;
+    grid_to_bricks_kernel<<<grid_for(nb, 256), 256, 0, S(stream)>>>(d, grid, bricks, pad, nb);
+    return check_launch("grid_to_bricks_kernel");
+}
+
+int rn_bricks_to_grid(const RnParams *p, const float *bricks, float *grid, int apply_sigmoid, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    const int64_t n = (int64_t)d.gx * d.gy * d.gz;
+    bricks_to_grid_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(d, bricks, grid, apply_sigmoid, n);
+    return check_launch("bricks_to_grid_kernel");
+}
+
 int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *features,
                        const int32_t *view_ids, int32_t n_feature_slots, const float *P,
                        const float *P_inv, const float *centre, const float *axis_centres, float *starts,
@@ -439,10 +492,10 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
             return fail(RN_ERR_UNSUPPORTED, "feature volume too large for int32 element offsets");
     }
     if ((starts == nullptr) != (ends == nullptr)) return fail(RN_ERR_SHAPE, "starts and ends must both be given or both NULL");
-    DdaArgs da = {};
+    DdaCodesArgs da = {};
     da.ray_idxs = ray_idxs; da.P_inv = P_inv; da.centre = centre; da.starts = starts; da.ends = ends;
     da.hdr = ray_hdr; da.codes = codes; da.count = count; da.n_rays = n_rays;
-    rc = launch_dda<true>(d, da, S(stream));
+    rc = launch_dda_codes(d, da, S(stream));
     if (rc) return rc;
     SimMapArgs a = {};
     a.ray_idxs = ray_idxs; a.features = features; a.view_ids = view_ids; a.P = P; a.P_inv = P_inv; a.centre = centre;
@@ -450,30 +503,67 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
     return launch_simmap<false>(d, a, d.M, true, S(stream));
 }
 
+int rn_engine_bin_rays(const RnParams *p, const int32_t *count, int64_t n_rays, int64_t seg_len, int32_t *order,
+                       uint64_t *class_scratch, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, true);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(class_scratch, 0, sizeof(uint64_t) * 2 * RN_NCLASS, S(stream));
+    if (e != cudaSuccess) return fail(RN_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+    if (n_rays <= 0) return RN_OK;
+    if (n_rays >= (1ll << 31)) return fail(RN_ERR_UNSUPPORTED, "more than 2^31 rays per rank");
+    // the tiled enumeration needs whole images of whole 8 x 8 tiles; anything else keeps ray order
+    const int H = d.H;
+    if (seg_len > 0 && (H <= 0 || (H % 8) != 0 || (seg_len % H) != 0 || ((seg_len / H) % 8) != 0 || (n_rays % seg_len) != 0))
+        seg_len = 0;
+    unsigned long long *counts = reinterpret_cast<unsigned long long *>(class_scratch);
+    bin_hist_kernel<<<grid_for(n_rays, 256), 256, 0, S(stream)>>>(count, n_rays, counts);
+    rc = check_launch("bin_hist_kernel");
+    if (rc) return rc;
+    bin_scatter_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, S(stream)>>>(count, n_rays, seg_len, H, counts,
+                                                                              counts + RN_NCLASS, order);
+    return check_launch("bin_scatter_kernel");
+}
+
 int rn_engine_bp_iteration(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes,
                            const int32_t *count, const float *s_hat, float *msgs, const float *acc_in,
-                           float *acc_out, int32_t max_count, int64_t n_rays, void *stream) {
+                           float *acc_out, const int32_t *order, const int64_t *class_offsets,
+                           int32_t first_sweep, int32_t max_count, int64_t n_rays, void *stream) {
     RnDev d;
     int rc = make_dev(p, d, true, false, true);
     if (rc) return rc;
     if (max_count <= 0 || max_count > d.M) max_count = d.M;
-    BpArgs a = {};
-    a.S = s_hat; a.hdr = ray_hdr; a.codes = codes; a.count = count; a.acc_in = acc_in; a.msgs = msgs;
-    a.acc_out = acc_out; a.n_rays = n_rays;
-    return launch_bp<true>(d, a, max_count, S(stream));
+    Bp2Args a = {};
+    a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.msgs = msgs; a.acc_in = acc_in;
+    a.acc_out = acc_out;
+    if (!order || !class_offsets) {   // no binning: one launch sized for the longest ray
+        a.first = 0; a.n = n_rays;
+        return launch_bp2<false>(d, a, first_sweep != 0, (max_count + RN_CHUNK - 1) / RN_CHUNK, S(stream));
+    }
+    a.order = order;
+    for (int c = 1; c < RN_NCLASS; c++) {   // class 0 (count <= 1) is skipped by BP
+        a.first = class_offsets[c];
+        a.n = class_offsets[c + 1] - class_offsets[c];
+        if (a.first < 0 || a.n < 0 || a.first + a.n > n_rays) return fail(RN_ERR_SHAPE, "class_offsets out of range");
+        rc = launch_bp2<false>(d, a, first_sweep != 0, c, S(stream));
+        if (rc) return rc;
+    }
+    return RN_OK;
 }
 
 int rn_engine_depth(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count,
                     const float *s_hat, const float *msgs, const float *acc, const float *axis_centres,
-                    const float *centre, float *depth_map, int32_t max_count, int64_t n_rays, void *stream) {
+                    const float *centres, const int64_t *seg_starts, int32_t n_seg, float *depth_map,
+                    float *S_new, int64_t n_rays, void *stream) {
     RnDev d;
     int rc = make_dev(p, d, true, false, true);
     if (rc) return rc;
-    if (max_count <= 0 || max_count > d.M) max_count = d.M;
-    DepthArgs a = {};
-    a.S = s_hat; a.hdr = ray_hdr; a.codes = codes; a.count = count; a.acc = acc; a.msgs = msgs;
-    a.axes = axis_centres; a.centre = centre; a.depth_map = depth_map; a.n_rays = n_rays;
-    return launch_depth<true>(d, a, max_count, S(stream));
+    if (n_seg < 1) return fail(RN_ERR_SHAPE, "n_seg must be at least 1");
+    Depth2Args a = {};
+    a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.msgs = msgs; a.acc = acc;
+    a.axes = axis_centres; a.centres = centres; a.seg_starts = (n_seg > 1) ? seg_starts : nullptr; a.n_seg = n_seg;
+    a.depth_map = depth_map; a.S_new = S_new; a.n_rays = n_rays;
+    return launch_depth2<false>(d, a, S(stream));
 }
 
 int rn_engine_expand_indices(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes,

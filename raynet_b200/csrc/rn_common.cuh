@@ -28,8 +28,11 @@ struct RnDev {
     int fh, fw;         // feature-map extents H+p+1, W+p+1 (feature_similarities.cu:74-75)
     int shift;          // padding - (padding-1)/2     (feature_similarities.cu:49-50)
     int npairs;         // (V*(V-1))/2                 (feature_similarities.cu:106)
-    int code_stride;    // bytes per ray in the step-code array
+    int code_stride;    // bytes per ray in the step-code array (32 per 128-voxel chunk)
     int row_stride;     // floats per ray in S / msgs rows (= M for the reference layout)
+    // bricked accumulator layout (rn_engine.cuh): 4x4x2-voxel lines of four 2x2x2 sectors
+    int bbx, bby, blz;  // bricks along x, bricks along y, lines along z (= ceil(G/4), ceil(G/4), ceil(G/2))
+    int bsx, bsy;       // element strides of one brick step along x / y (bby*blz*32, blz*32)
 };
 
 __device__ __forceinline__ float rn_clampf(float x, float a, float b) {
@@ -82,6 +85,15 @@ __device__ __forceinline__ float rn_ld_acc(const float *p) {
 // Fire-and-forget scatter-add (RED, no return value), resolved in L2.
 __device__ __forceinline__ void rn_red_add(float *p, float v) {
     uint64_t pol = rn_policy_evict_last();
+    asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
+}
+// The same two with a caller-held policy descriptor (created once per kernel).
+__device__ __forceinline__ float rn_ld_acc_pol(const float *p, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void rn_red_add_pol(float *p, float v, uint64_t pol) {
     asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
 }
 

@@ -1,31 +1,23 @@
-// rn_kernels.cuh -- the sm_100a kernels of the RayNet hot path.
+// rn_kernels.cuh -- front-end and reference-layout kernels of the RayNet hot path (sm_100a).
 //
 //   dda_kernel      thread-per-ray Amanatides-Woo traversal (a3), optionally fused with
-//                   sample_in_bbox (a1).  Emits either the reference's int32 [M][3]
-//                   lists or the resident 2-bit step codes.
+//                   sample_in_bbox (a1), emitting the reference's int32 [M][3] lists (the
+//                   resident step-code flavour lives in rn_engine.cuh).
 //   simmap_kernel   warp-per-ray: sample_in_bbox (a1) -> plane-sweep similarity + softmax
-//                   (a2) -> plane->voxel interpolation (a4) -> clip_and_renorm.
-//   bp_kernel       warp-per-ray ray-potential sum-product sweep (a5, a6): forward
-//                   product / prefix scans and a backward suffix scan with warp
-//                   shuffles, 128-bit row loads/stores, RED scatter-add into the grid.
-//   depth_kernel    warp-per-ray depth re-estimation + arg-max -> depth (a8, a9).
-//
-// Work decomposition for the warp-per-ray kernels: a ray of L voxels is cut into chunks
-// of 128 consecutive voxels; in a chunk lane l owns voxels 4l..4l+3, so the per-ray rows
-// (s_hat, messages) are read and written as one 128-bit access per lane, fully coalesced.
-// Scans are "4 sequential + one 5-step warp scan", i.e. 5 shuffles per 128 voxels per
-// scan.  Everything a ray needs between its forward and backward phase stays in
-// registers (NCH chunks, template parameter chosen on the host from the longest ray).
+//                   (a2) -> plane->voxel interpolation (a4) -> clip_and_renorm; serves both
+//                   the reference layout (kAos) and the resident pipeline.
+//   small stand-alone kernels (sample points, planes->voxels on given S, fills, ...).
+// The BP sweep and the depth pass (both layouts) are bp2_kernel / depth2_kernel in
+// rn_engine.cuh.
 #pragma once
 
 #include "rn_common.cuh"
+#include "rn_engine.cuh"
 
 // =======================================================================================
 // a3. DDA  (ray_tracing.pyx:99-199 == ray_tracing.cu:15-142), thread per ray
 // =======================================================================================
-template <bool kCodes>
-__device__ __forceinline__ int rn_dda(const RnDev &p, const float *rs_in, const float *re_in,
-                                      int32_t *idx_row, uint32_t *hdr, uint32_t *code_words) {
+__device__ __forceinline__ int rn_dda(const RnDev &p, const float *rs_in, const float *re_in, int32_t *idx_row) {
     const float EPS = 1e-2f;
     float s[3], e[3], ray[3], tMax[3], tDelta[3];
     int step[3], cur[3], last[3];
@@ -42,10 +34,6 @@ __device__ __forceinline__ int rn_dda(const RnDev &p, const float *rs_in, const 
         cur[a] = (int)floorf(s[a] / p.bin[a]);
         last[a] = (int)floorf(e[a] / p.bin[a]);
     }
-    if (kCodes) {
-        hdr[0] = 0;
-        hdr[1] = 0;
-    }
     bool inside = cur[0] >= 0 && cur[0] < g[0] && cur[1] >= 0 && cur[1] < g[1] && cur[2] >= 0 && cur[2] < g[2];
     if (!inside) return 0;
 #pragma unroll
@@ -59,16 +47,9 @@ __device__ __forceinline__ int rn_dda(const RnDev &p, const float *rs_in, const 
             tDelta[a] = ((float)step[a] * p.bin[a]) / ray[a];
         }
     }
-    uint32_t word = 3u;   // voxel 0: "no step"
-    if (kCodes) {
-        hdr[0] = (uint32_t)cur[0] | ((uint32_t)cur[1] << 16);
-        hdr[1] = (uint32_t)cur[2] | ((step[0] < 0 ? 1u : 0u) << 16) | ((step[1] < 0 ? 1u : 0u) << 17) |
-                 ((step[2] < 0 ? 1u : 0u) << 18);
-    } else {
-        idx_row[0] = cur[0];
-        idx_row[1] = cur[1];
-        idx_row[2] = cur[2];
-    }
+    idx_row[0] = cur[0];
+    idx_row[1] = cur[1];
+    idx_row[2] = cur[2];
     int ii = 1;
     const int M = p.M;
     while (!(cur[0] == last[0] && cur[1] == last[1] && cur[2] == last[2]) && ii < M) {
@@ -87,23 +68,10 @@ __device__ __forceinline__ int rn_dda(const RnDev &p, const float *rs_in, const 
         tMax[0] = ax ? tMax[0] + tDelta[0] : tMax[0];
         tMax[1] = ay ? tMax[1] + tDelta[1] : tMax[1];
         tMax[2] = az ? tMax[2] + tDelta[2] : tMax[2];
-        if (kCodes) {
-            int pos = ii & 15;
-            word = (pos == 0) ? (uint32_t)a : (word | ((uint32_t)a << (2 * pos)));
-            if (pos == 15) code_words[ii >> 4] = word;
-        } else {
-            idx_row[3 * ii + 0] = cur[0];
-            idx_row[3 * ii + 1] = cur[1];
-            idx_row[3 * ii + 2] = cur[2];
-        }
+        idx_row[3 * ii + 0] = cur[0];
+        idx_row[3 * ii + 1] = cur[1];
+        idx_row[3 * ii + 2] = cur[2];
         ii++;
-    }
-    if (kCodes) {
-        int lastpos = (ii - 1) & 15;
-        if (lastpos != 15) {   // flush the partial word, padding the tail with "no step"
-            word |= (0xffffffffu << (2 * (lastpos + 1)));
-            code_words[(ii - 1) >> 4] = word;
-        }
     }
     return ii;
 }
@@ -112,14 +80,11 @@ struct DdaArgs {
     const int32_t *ray_idxs;   // if non-null: start/end come from sample_in_bbox (and are written out)
     const float *P_inv, *centre;
     float *starts, *ends;      // inputs when ray_idxs == null; optional outputs otherwise
-    int32_t *idx;              // [n][M][3]      (kCodes == false)
-    uint32_t *hdr;             // [n][2]         (kCodes == true)
-    uint8_t *codes;            // [n][code_stride]
+    int32_t *idx;              // [n][M][3]
     int32_t *count;            // [n]
     int64_t n_rays;
 };
 
-template <bool kCodes>
 __global__ void __launch_bounds__(128) dda_kernel(RnDev p, DdaArgs a) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n_rays) return;
@@ -145,100 +110,7 @@ __global__ void __launch_bounds__(128) dda_kernel(RnDev p, DdaArgs a) {
             re[i] = a.ends[3 * r + i];
         }
     }
-    int c;
-    if (kCodes)
-        c = rn_dda<true>(p, rs, re, nullptr, a.hdr + 2 * r, (uint32_t *)(a.codes + r * (int64_t)p.code_stride));
-    else
-        c = rn_dda<false>(p, rs, re, a.idx + r * (int64_t)p.M * 3, nullptr, nullptr);
-    a.count[r] = c;
-}
-
-// =======================================================================================
-// Per-warp decoding of a ray's voxel coordinates, chunk by chunk
-// =======================================================================================
-struct RayDecoder {
-    int x0, y0, z0;   // first voxel
-    int sx, sy, sz;   // step signs
-    int bx, by, bz;   // steps taken per axis before the current chunk
-};
-
-__device__ __forceinline__ void rn_decoder_init(RayDecoder &d, const uint32_t *hdr) {
-    uint32_t h0 = __ldg(hdr), h1 = __ldg(hdr + 1);
-    d.x0 = h0 & 0xffff;
-    d.y0 = h0 >> 16;
-    d.z0 = h1 & 0xffff;
-    d.sx = (h1 & (1u << 16)) ? -1 : 1;
-    d.sy = (h1 & (1u << 17)) ? -1 : 1;
-    d.sz = (h1 & (1u << 18)) ? -1 : 1;
-    d.bx = d.by = d.bz = 0;
-}
-
-// Coordinates of the lane's 4 voxels of chunk c.  Voxels >= L get coordinates of no use
-// (callers mask on the voxel index).  Must be called by the full warp, chunks in order.
-template <bool kAos>
-__device__ __forceinline__ void rn_decode_chunk(RayDecoder &d, const uint8_t *code_row, const int32_t *idx_row,
-                                                int c, int lane, int L, int vx[4], int vy[4], int vz[4]) {
-    const int i0 = c * RN_CHUNK + lane * RN_VOX_PER_LANE;
-    if (kAos) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int i = i0 + j;
-            bool ok = i < L;
-            vx[j] = ok ? __ldg(idx_row + 3 * i + 0) : 0;
-            vy[j] = ok ? __ldg(idx_row + 3 * i + 1) : 0;
-            vz[j] = ok ? __ldg(idx_row + 3 * i + 2) : 0;
-        }
-    } else {
-        uint32_t cb = (i0 < L) ? rn_ld_stream_u8(code_row + c * 32 + lane) : 0xffu;
-        uint32_t run = 0, cnt[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t f = (cb >> (2 * j)) & 3u;
-            run += (f == 3u) ? 0u : (1u << (10 * f));
-            cnt[j] = run;
-        }
-        uint32_t incl = rn_warp_incl_scan_u32(run, lane);
-        uint32_t excl = incl - run;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t pk = excl + cnt[j];
-            vx[j] = d.x0 + d.sx * (d.bx + (int)(pk & 1023u));
-            vy[j] = d.y0 + d.sy * (d.by + (int)((pk >> 10) & 1023u));
-            vz[j] = d.z0 + d.sz * (d.bz + (int)(pk >> 20));
-        }
-        uint32_t tot = __shfl_sync(RN_FULL_MASK, incl, 31);
-        d.bx += (int)(tot & 1023u);
-        d.by += (int)((tot >> 10) & 1023u);
-        d.bz += (int)(tot >> 20);
-    }
-}
-
-// Row access: the resident layout guarantees 16-byte aligned rows (vector path); the
-// reference layout (arbitrary M) uses scalar accesses.
-template <bool kVec>
-__device__ __forceinline__ void rn_load_row4(const float *row, int i0, int L, float v[4]) {
-    if (kVec) {
-        if (i0 < L) {
-            float4 t = rn_ld_stream4(row + i0);
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
-            v[0] = v[1] = v[2] = v[3] = 0.f;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = (i0 + j < L) ? row[i0 + j] : 0.f;
-    }
-}
-template <bool kVec>
-__device__ __forceinline__ void rn_store_row4(float *row, int i0, int L, const float v[4]) {
-    if (kVec) {
-        // rows are padded to a multiple of 4 floats: the tail of the last quad is scratch
-        if (i0 < L) rn_st_stream4(row + i0, make_float4(v[0], v[1], v[2], v[3]));
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (i0 + j < L) row[i0 + j] = v[j];
-    }
+    a.count[r] = rn_dda(p, rs, re, a.idx + r * (int64_t)p.M * 3);
 }
 
 // =======================================================================================
@@ -445,15 +317,19 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
         for (int i = 0; i < 3; i++) ray_norm += ray[i] * ray[i];
         const float pstep = (1.0f - 0.0f) / (float)(D - 1);
 
-        RayDecoder dec;
-        const uint8_t *code_row = nullptr;
+        // voxel (c, j) of this lane = c*128 + 32*j + lane: lanes walk CONSECUTIVE voxels, so the
+        // row stores below are plain coalesced 128-byte warp stores and the step codes decode
+        // with popc (rn_engine.cuh)
+        RayHead head = {0, 0, 0, 1, 1, 1};
+        const uint2 *words = nullptr;
         const int32_t *idx_row = nullptr;
         if (kAos) {
             idx_row = a.idx + r * (int64_t)p.M * 3;
         } else {
-            rn_decoder_init(dec, a.hdr + 2 * r);
-            code_row = a.codes + r * (int64_t)p.code_stride;
+            head = rn_ray_head(a.hdr + 2 * r);
+            words = reinterpret_cast<const uint2 *>(a.codes + r * (int64_t)p.code_stride);
         }
+        StepCount before = {0, 0, 0};
 
         float val[NCH][4];
         float lsum = 0.f;
@@ -462,15 +338,19 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             if (c < nch) {
-                int vx[4], vy[4], vz[4];
-                rn_decode_chunk<kAos>(dec, code_row, idx_row, c, lane, L, vx, vy, vz);
-                const int i0 = c * RN_CHUNK + lane * RN_VOX_PER_LANE;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
+                    const int i = c * RN_CHUNK + 32 * j + lane;
+                    int vx = 0, vy = 0, vz = 0;
+                    if (kAos) {
+                        if (i < L) { vx = __ldg(idx_row + 3 * i); vy = __ldg(idx_row + 3 * i + 1); vz = __ldg(idx_row + 3 * i + 2); }
+                    } else {
+                        const uint2 cw = __ldg(words + c * 4 + j);
+                        rn_decode_pair(head, cw.x, cw.y, lane, before, vx, vy, vz);
+                    }
                     float out = 0.f;
-                    if (i0 + j < L) {
-                        float cc[3] = {__ldg(a.axes + vx[j]), __ldg(a.axes + p.gx + vy[j]),
-                                       __ldg(a.axes + p.gx + p.gy + vz[j])};
+                    if (i < L) {
+                        float cc[3] = {__ldg(a.axes + vx), __ldg(a.axes + p.gx + vy), __ldg(a.axes + p.gx + p.gy + vz)};
                         float sum = 0.f;
 #pragma unroll
                         for (int t = 0; t < 3; t++) {
@@ -489,7 +369,7 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
                         float c1 = (float)(1.0 - (double)(left_d / (left_d + right_d)));
                         float c2 = (float)(1.0 - (double)(right_d / (left_d + right_d)));
                         out = c1 * sS[left] + c2 * sS[left + 1];
-                        if (out > bestv) { bestv = out; besti = i0 + j; bestx = vx[j]; besty = vy[j]; bestz = vz[j]; }
+                        if (out > bestv) { bestv = out; besti = i; bestx = vx; besty = vy; bestz = vz; }
                     }
                     val[c][j] = out;
                     lsum += out;
@@ -502,16 +382,12 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             if (c < nch) {
-                const int i0 = c * RN_CHUNK + lane * RN_VOX_PER_LANE;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
+                    const int i = c * RN_CHUNK + 32 * j + lane;
                     float v = val[c][j] / srsum;
-                    val[c][j] = v;
-                }
-                if (a.S_vox) rn_store_row4<!kAos>(a.S_vox + r * (int64_t)p.row_stride, i0, L, val[c]);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    float v = (i0 + j < L) ? rn_clampf(val[c][j], 1e-5f, 0.99999f) : 0.f;
+                    if (a.S_vox && i < L) a.S_vox[r * (int64_t)p.row_stride + i] = v;
+                    v = (i < L) ? rn_clampf(v, 1e-5f, 0.99999f) : 0.f;
                     val[c][j] = v;
                     csum += v;
                 }
@@ -522,10 +398,11 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
                 if (c < nch) {
-                    const int i0 = c * RN_CHUNK + lane * RN_VOX_PER_LANE;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) val[c][j] = val[c][j] / csum;
-                    rn_store_row4<!kAos>(a.s_hat + r * (int64_t)p.row_stride, i0, L, val[c]);
+                    for (int j = 0; j < 4; j++) {
+                        const int i = c * RN_CHUNK + 32 * j + lane;
+                        if (i < L) a.s_hat[r * (int64_t)p.row_stride + i] = val[c][j] / csum;
+                    }
                 }
             }
         }
@@ -546,307 +423,6 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
                 for (int i = 0; i < 3; i++) { float dd = cc[i] - sC[i]; sum += dd * dd; }
                 a.depth_vox[r] = sqrtf(sum);
             }
-        }
-    }
-}
-
-// =======================================================================================
-// a5 + a6. one ray-potential BP sweep, warp per ray
-// =======================================================================================
-struct BpArgs {
-    const float *S;            // kEngine: s_hat (already clip_and_renorm'ed); else raw S_voxel_space
-    const int32_t *idx;        // !kEngine
-    const uint32_t *hdr;       // kEngine
-    const uint8_t *codes;      // kEngine
-    const int32_t *count;
-    const float *acc_in;
-    float *msgs;               // in/out
-    float *acc_out;
-    int64_t n_rays;
-};
-
-template <int NCH, bool kEngine>
-__global__ void __launch_bounds__(256) bp_kernel(RnDev p, BpArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= a.n_rays) return;
-    const int L = __ldg(a.count + r);
-    if (L <= 1) return;   // mrf_np.py:299-301
-    const int nch = (L + RN_CHUNK - 1) / RN_CHUNK;
-
-    const float *s_row = a.S + r * (int64_t)p.row_stride;
-    float *m_row = a.msgs + r * (int64_t)p.row_stride;
-    RayDecoder dec;
-    const uint8_t *code_row = nullptr;
-    const int32_t *idx_row = nullptr;
-    if (kEngine) {
-        rn_decoder_init(dec, a.hdr + 2 * r);
-        code_row = a.codes + r * (int64_t)p.code_stride;
-    } else {
-        idx_row = a.idx + r * (int64_t)p.M * 3;
-    }
-
-    // ---- phase A: issue every load of the ray (independent of the scans) -----------------
-    float sv[NCH][4], ov[NCH][4];
-    int lin[NCH][4];
-    float rawsum = 0.f;
-#pragma unroll
-    for (int c = 0; c < NCH; c++) {
-        if (c < nch) {
-            const int i0 = c * RN_CHUNK + lane * RN_VOX_PER_LANE;
-            int vx[4], vy[4], vz[4];
-            rn_decode_chunk<!kEngine>(dec, code_row, idx_row, c, lane, L, vx, vy, vz);
-            float mv[4];
-            rn_load_row4<kEngine>(s_row, i0, L, sv[c]);
-            rn_load_row4<kEngine>(m_row, i0, L, mv);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const bool ok = i0 + j < L;
-                lin[c][j] = ok ? rn_lin(p, vx[j], vy[j], vz[j]) : 0;
-                float acc = ok ? rn_ld_acc(a.acc_in + lin[c][j]) : 0.f;
-                // invalid voxels: o = 0 -> factor (1-o) = 1 and a = 0: neutral in every scan
-                ov[c][j] = ok ? rn_occ_to_ray(acc, mv[j]) : 0.f;
-                if (!kEngine) {
-                    sv[c][j] = ok ? rn_clampf(sv[c][j], 1e-5f, 0.99999f) : 0.f;
-                    rawsum += sv[c][j];
-                } else {
-                    sv[c][j] = ok ? sv[c][j] : 0.f;
-                }
-            }
-        }
-    }
-    if (!kEngine) {   // clip_and_renorm on the fly (mrf_np.py:4-8, :306)
-        rawsum = rn_warp_sum(rawsum);
-#pragma unroll
-        for (int c = 0; c < NCH; c++)
-            if (c < nch) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) sv[c][j] = sv[c][j] / rawsum;
-            }
-    }
-
-    // ---- phase B: forward scans: cp_i = prod_{k<i}(1-o_k), pre_i = sum_{j<i} a_j ----------
-    float cps[NCH][4], pre[NCH][4], tot[NCH];
-    float carry_cp = 1.f, carry_pre = 0.f;
-#pragma unroll
-    for (int c = 0; c < NCH; c++) {
-        tot[c] = 0.f;
-        if (c < nch) {
-            float lp[4];
-            lp[0] = 1.f - ov[c][0];
-            lp[1] = lp[0] * (1.f - ov[c][1]);
-            lp[2] = lp[1] * (1.f - ov[c][2]);
-            lp[3] = lp[2] * (1.f - ov[c][3]);
-            float inc = rn_warp_incl_scan_mul(lp[3], lane);
-            float exc = __shfl_up_sync(RN_FULL_MASK, inc, 1);
-            if (lane == 0) exc = 1.f;
-            const float base = carry_cp * exc;
-            carry_cp = carry_cp * __shfl_sync(RN_FULL_MASK, inc, 31);
-            float av[4], la[4];
-            cps[c][0] = base * sv[c][0];
-            cps[c][1] = (base * lp[0]) * sv[c][1];
-            cps[c][2] = (base * lp[1]) * sv[c][2];
-            cps[c][3] = (base * lp[2]) * sv[c][3];
-#pragma unroll
-            for (int j = 0; j < 4; j++) av[j] = ov[c][j] * cps[c][j];
-            la[0] = av[0];
-            la[1] = la[0] + av[1];
-            la[2] = la[1] + av[2];
-            la[3] = la[2] + av[3];
-            float sinc = rn_warp_incl_scan_add(la[3], lane);
-            float sexc = sinc - la[3];
-            const float pbase = carry_pre + sexc;
-            pre[c][0] = pbase;
-            pre[c][1] = pbase + la[0];
-            pre[c][2] = pbase + la[1];
-            pre[c][3] = pbase + la[2];
-            tot[c] = __shfl_sync(RN_FULL_MASK, sinc, 31);
-            carry_pre += tot[c];
-        }
-    }
-
-    // ---- phase C: backward suffix scan, messages, scatter-add ----------------------------
-    float carry_suf = 0.f;
-#pragma unroll
-    for (int c = NCH - 1; c >= 0; c--) {
-        if (c < nch) {
-            const int i0 = c * RN_CHUNK + lane * RN_VOX_PER_LANE;
-            float av[4], ra[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) av[j] = ov[c][j] * cps[c][j];
-            ra[3] = av[3];
-            ra[2] = av[2] + ra[3];
-            ra[1] = av[1] + ra[2];
-            ra[0] = av[0] + ra[1];
-            float rinc = rn_warp_incl_rscan_add(ra[0], lane);
-            const float sbase = carry_suf + (rinc - ra[0]);
-            float suf[4] = {sbase + ra[1], sbase + ra[2], sbase + ra[3], sbase};
-            float msg[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float pos = pre[c][j] + cps[c][j];
-                float neg = pre[c][j] + suf[j] / (1.f - ov[c][j]);
-                msg[j] = logf(pos) - logf(neg);   // == log p - log(1-p), p = pos/(pos+neg)
-            }
-            rn_store_row4<kEngine>(m_row, i0, L, msg);
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (i0 + j < L) rn_red_add(a.acc_out + lin[c][j], msg[j]);
-            carry_suf += tot[c];
-        }
-    }
-}
-
-// =======================================================================================
-// a8 + a9. depth re-estimation (+ arg-max -> depth), warp per ray
-// =======================================================================================
-struct DepthArgs {
-    const float *S;            // kEngine: s_hat; else raw S_voxel_space
-    const int32_t *idx;
-    const uint32_t *hdr;
-    const uint8_t *codes;
-    const int32_t *count;
-    const float *acc;
-    const float *msgs;
-    const float *axes;         // needed when depth_map != null
-    const float *centre;
-    float *S_new;              // [n][row_stride] optional out (normalised, zero beyond count)
-    float *depth_map;          // [n] optional out
-    int64_t n_rays;
-};
-
-template <int NCH, bool kEngine>
-__global__ void __launch_bounds__(256) depth_kernel(RnDev p, DepthArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= a.n_rays) return;
-    const int L = __ldg(a.count + r);
-    const int nch = (max(L, 0) + RN_CHUNK - 1) / RN_CHUNK;
-    const float *s_row = a.S + r * (int64_t)p.row_stride;
-    const float *m_row = a.msgs + r * (int64_t)p.row_stride;
-    RayDecoder dec;
-    dec.x0 = dec.y0 = dec.z0 = 0;
-    const uint8_t *code_row = nullptr;
-    const int32_t *idx_row = nullptr;
-    if (kEngine) {
-        rn_decoder_init(dec, a.hdr + 2 * r);
-        code_row = a.codes + r * (int64_t)p.code_stride;
-    } else {
-        idx_row = a.idx + r * (int64_t)p.M * 3;
-    }
-    int fx = 0, fy = 0, fz = 0;   // voxel of slot 0 (what the reference reads for an all-zero row)
-    if (L >= 1) {
-        if (kEngine) { fx = dec.x0; fy = dec.y0; fz = dec.z0; }
-        else { fx = __ldg(idx_row); fy = __ldg(idx_row + 1); fz = __ldg(idx_row + 2); }
-    }
-
-    float av[NCH][4];
-    float bestv = -INFINITY;
-    int besti = 0, bestx = fx, besty = fy, bestz = fz;
-    float asum = 0.f;
-    if (L > 1) {   // mrf_np.py:376-377: rays with count <= 1 keep an all-zero row
-        float sv[NCH][4], ov[NCH][4];
-        int cx[NCH][4], cy[NCH][4], cz[NCH][4];
-        float rawsum = 0.f;
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            if (c < nch) {
-                const int i0 = c * RN_CHUNK + lane * RN_VOX_PER_LANE;
-                rn_decode_chunk<!kEngine>(dec, code_row, idx_row, c, lane, L, cx[c], cy[c], cz[c]);
-                float mv[4];
-                rn_load_row4<kEngine>(s_row, i0, L, sv[c]);
-                rn_load_row4<kEngine>(m_row, i0, L, mv);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const bool ok = i0 + j < L;
-                    float acc = ok ? rn_ld_acc(a.acc + rn_lin(p, cx[c][j], cy[c][j], cz[c][j])) : 0.f;
-                    ov[c][j] = ok ? rn_occ_to_ray(acc, mv[j]) : 0.f;
-                    if (!kEngine) {
-                        sv[c][j] = ok ? rn_clampf(sv[c][j], 1e-5f, 0.99999f) : 0.f;
-                        rawsum += sv[c][j];
-                    } else {
-                        sv[c][j] = ok ? sv[c][j] : 0.f;
-                    }
-                }
-            }
-        }
-        if (!kEngine) {
-            rawsum = rn_warp_sum(rawsum);
-#pragma unroll
-            for (int c = 0; c < NCH; c++)
-                if (c < nch) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) sv[c][j] = sv[c][j] / rawsum;
-                }
-        }
-        float carry_cp = 1.f;
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            if (c < nch) {
-                const int i0 = c * RN_CHUNK + lane * RN_VOX_PER_LANE;
-                float lp[4];
-                lp[0] = 1.f - ov[c][0];
-                lp[1] = lp[0] * (1.f - ov[c][1]);
-                lp[2] = lp[1] * (1.f - ov[c][2]);
-                lp[3] = lp[2] * (1.f - ov[c][3]);
-                float inc = rn_warp_incl_scan_mul(lp[3], lane);
-                float exc = __shfl_up_sync(RN_FULL_MASK, inc, 1);
-                if (lane == 0) exc = 1.f;
-                const float base = carry_cp * exc;
-                carry_cp = carry_cp * __shfl_sync(RN_FULL_MASK, inc, 31);
-                av[c][0] = ov[c][0] * (base * sv[c][0]);
-                av[c][1] = ov[c][1] * ((base * lp[0]) * sv[c][1]);
-                av[c][2] = ov[c][2] * ((base * lp[1]) * sv[c][2]);
-                av[c][3] = ov[c][3] * ((base * lp[2]) * sv[c][3]);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (i0 + j < L) {
-                        asum += av[c][j];
-                        if (av[c][j] > bestv) {
-                            bestv = av[c][j]; besti = i0 + j;
-                            bestx = cx[c][j]; besty = cy[c][j]; bestz = cz[c][j];
-                        }
-                    }
-                }
-            }
-        }
-        asum = rn_warp_sum(asum);
-    }
-    if (a.S_new) {   // normalised distribution, zero beyond count (mrf_np.py:370, :378)
-        float *o_row = a.S_new + r * (int64_t)p.row_stride;
-        if (L > 1) {
-#pragma unroll
-            for (int c = 0; c < NCH; c++)
-                if (c < nch) {
-                    const int i0 = c * RN_CHUNK + lane * RN_VOX_PER_LANE;
-                    float v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) v[j] = av[c][j] / asum;
-                    rn_store_row4<kEngine>(o_row, i0, L, v);
-                }
-        }
-        const int zfrom = (L > 1) ? L : 0;
-        if (!kEngine)
-            for (int i = zfrom + lane; i < p.M; i += 32) o_row[i] = 0.f;
-    }
-    if (a.depth_map) {   // raynet_fp.py:193-226
-        if (L > 1) {
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                float ovv = __shfl_xor_sync(RN_FULL_MASK, bestv, d);
-                int oi = __shfl_xor_sync(RN_FULL_MASK, besti, d);
-                int ox = __shfl_xor_sync(RN_FULL_MASK, bestx, d);
-                int oy = __shfl_xor_sync(RN_FULL_MASK, besty, d);
-                int oz = __shfl_xor_sync(RN_FULL_MASK, bestz, d);
-                if (ovv > bestv || (ovv == bestv && oi < besti)) { bestv = ovv; besti = oi; bestx = ox; besty = oy; bestz = oz; }
-            }
-        }
-        if (lane == 0) {
-            float cc[3] = {__ldg(a.axes + bestx), __ldg(a.axes + p.gx + besty), __ldg(a.axes + p.gx + p.gy + bestz)};
-            float sum = 0.f;
-#pragma unroll
-            for (int i = 0; i < 3; i++) { float dd = cc[i] - __ldg(a.centre + i); sum += dd * dd; }
-            a.depth_map[r] = sqrtf(sum);
         }
     }
 }
@@ -900,30 +476,6 @@ __global__ void max_count_kernel(const int32_t *count, int64_t n, int32_t *out) 
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(RN_FULL_MASK, m, d));
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
-}
-
-// Expand resident step codes into the reference's dense int32 [M][3] lists (thread per ray).
-__global__ void expand_indices_kernel(RnDev p, const uint32_t *hdr, const uint8_t *codes, const int32_t *count,
-                                      int32_t *idx, int64_t n_rays) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rays) return;
-    int L = count[r];
-    int32_t *row = idx + r * (int64_t)p.M * 3;
-    uint32_t h0 = hdr[2 * r], h1 = hdr[2 * r + 1];
-    int x = h0 & 0xffff, y = h0 >> 16, z = h1 & 0xffff;
-    int sx = (h1 & (1u << 16)) ? -1 : 1, sy = (h1 & (1u << 17)) ? -1 : 1, sz = (h1 & (1u << 18)) ? -1 : 1;
-    const uint8_t *crow = codes + r * (int64_t)p.code_stride;
-    for (int i = 0; i < p.M; i++) {
-        if (i < L) {
-            uint32_t f = (crow[i >> 2] >> (2 * (i & 3))) & 3u;
-            if (f == 0) x += sx;
-            else if (f == 1) y += sy;
-            else if (f == 2) z += sz;
-            row[3 * i] = x; row[3 * i + 1] = y; row[3 * i + 2] = z;
-        } else {
-            row[3 * i] = 0; row[3 * i + 1] = 0; row[3 * i + 2] = 0;
-        }
-    }
 }
 
 // a1 stand-alone (thread per ray)

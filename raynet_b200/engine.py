@@ -4,15 +4,18 @@ Replaces the host loop of RayNetForwardPass.forward_pass (raynet/forward_pass.py
 which re-runs CNN + similarity + DDA + mapping on every BP sweep and bounces the messages
 through host memory per batch.  Here the front end runs ONCE per reference image and
 leaves per-ray state in HBM (step codes, clip_and_renorm'ed voxel distribution, messages);
-each BP sweep is one kernel launch over all rays of this rank; the two accumulator grids
-are double-buffered on the device.  The algorithm is the one of mrf_np.belief_propagation
-(mrf_np.py:243-330): synchronous sweeps, acc_prev <- acc_new, acc_new <- prior.
+each BP sweep is a handful of kernel launches (one per ray-length class) over all rays of
+this rank; the two accumulator grids are double-buffered on the device in a bricked layout.
+The algorithm is the one of mrf_np.belief_propagation (mrf_np.py:243-330): synchronous
+sweeps, acc_prev <- acc_new, acc_new <- prior.
 
 Multi-GPU (one process per GPU, torch.distributed / NCCL): rays are sharded, every rank
 accumulates a partial grid and the partials are summed with one all-reduce per sweep
 (valid because sweeps are synchronous/Jacobi).  Rank 0 seeds its partial
 with the prior so that the all-reduce result already is prior + sum of messages.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -31,9 +34,9 @@ class RayPotentialEngine(object):
     def __init__(self, M, D, n_views, F, H, W, padding, bbox, grid_shape, gamma=0.05, max_rays=0,
                  process_group=None, use_distributed=None):
         """M, D, n_views, F, H, W, padding, bbox, grid_shape: as perform_raynet_fp
-        (raynet_fp.py:10-41).  max_rays: capacity of the per-ray state on this rank."""
-        if M % 4 != 0:
-            raise AssertionError("resident layout needs max_voxels to be a multiple of 4")
+        (raynet_fp.py:10-41).  Rows of the per-ray state are padded to rn_row_stride(M) floats.
+        max_rays: capacity of the per-ray state on this rank."""
+        M = int(M)
         self.M, self.D, self.V, self.F, self.H, self.W, self.padding = M, D, n_views, F, H, W, padding
         self.grid_shape = tuple(int(g) for g in np.asarray(grid_shape).ravel())
         self.bbox = np.asarray(bbox, dtype=np.float32).ravel()
@@ -43,6 +46,8 @@ class RayPotentialEngine(object):
         self.params = _lib.make_params(M, D, n_views, F, H, W, padding, self.bbox, self.grid_shape)
         self.dev = device()
         self.code_stride = _lib.code_stride(M)
+        self.R = _lib.row_stride(M)             # floats per s_hat / msgs row
+        self.n_classes = _lib.num_classes()
         self.capacity = int(max_rays)
         self.n_rays = 0
         self.max_count = M
@@ -54,22 +59,27 @@ class RayPotentialEngine(object):
         self.rank = torch.distributed.get_rank(self.pg) if self.distributed else 0
         self.world = torch.distributed.get_world_size(self.pg) if self.distributed else 1
         self.launches = 0           # kernels launched by this engine (bench.py's gpu_launches)
-        G = int(np.prod(self.grid_shape))
-        self.G = G
+        self.G = int(np.prod(self.grid_shape))
+        self.GB = _lib.brick_elems(self.params)     # floats of a bricked accumulator (padding included)
         kw = dict(device=self.dev)
         n = self.capacity
         self.hdr = torch.zeros((n, 2), dtype=torch.int32, **kw)
         self.codes = torch.zeros((n, self.code_stride), dtype=torch.uint8, **kw)
         self.count = torch.zeros((n,), dtype=torch.int32, **kw)
-        self.s_hat = torch.zeros((n, M), dtype=torch.float32, **kw)
-        self.msgs = torch.zeros((n, M), dtype=torch.float32, **kw)
-        self.acc_prev = torch.full(self.grid_shape, self.prior, dtype=torch.float32, **kw)
-        self.acc_new = torch.empty(self.grid_shape, dtype=torch.float32, **kw)
+        self.s_hat = torch.empty((n, self.R), dtype=torch.float32, **kw)
+        self.msgs = torch.empty((n, self.R), dtype=torch.float32, **kw)
+        self.order = torch.zeros((n,), dtype=torch.int32, **kw)
+        self.acc_prev = torch.full((self.GB,), self.prior, dtype=torch.float32, **kw)
+        self.acc_new = torch.empty((self.GB,), dtype=torch.float32, **kw)
         self.axes = torch.zeros((sum(self.grid_shape),), dtype=torch.float32, **kw)
-        self._max_count_dev = torch.zeros((1,), dtype=torch.int32, **kw)
+        self._class_scratch = torch.zeros((2 * self.n_classes,), dtype=torch.int64, **kw)
+        self._class_offsets = None  # host int64 [n_classes + 1] (ctypes array) once rays are binned
+        self.class_sizes = None
+        self._centres = None
+        self._seg_starts = None
         self._axes_set = False
         self.iterations_done = 0
-        self.sweep_events = None    # bench.py: list of (start, end) CUDA events around each sweep kernel
+        self.sweep_events = None    # bench.py: list of (start, end) CUDA events around each sweep
 
     # ------------------------------------------------------------------ setup
     def set_voxel_grid(self, voxel_grid):
@@ -91,12 +101,17 @@ class RayPotentialEngine(object):
         self._axes_set = True
 
     def reset(self):
-        """Messages to 0, accumulator to the prior (mrf_np.py:275-292)."""
-        self.msgs.zero_()
-        self.acc_prev.fill_(self.prior)
+        """Forget the rays; messages count as 0 (the first sweep does not read them) and the
+        accumulator is back at the prior (mrf_np.py:275-292)."""
+        _lib.call("rn_fill_f32", _ptr(self.acc_prev), self.prior, self.GB, current_stream_ptr())
+        self.launches += 1
         self.iterations_done = 0
         self.n_rays = 0
         self.segments = []
+        self._class_offsets = None
+        self.class_sizes = None
+        self._centres = None
+        self._seg_starts = None
 
     # ------------------------------------------------------------------ front end
     def add_image(self, ray_idxs, features, P, P_inv, centre, view_ids=None, n_feature_slots=None,
@@ -122,30 +137,47 @@ class RayPotentialEngine(object):
         self.launches += 2
         self.segments.append((start, n, centre))
         self.n_rays = start + n
+        self._class_offsets = None
         return (starts, ends) if keep_start_end else None
 
     def finalize_frontend(self):
-        """One device->host read of the longest ray so the sweep kernels are instantiated for
-        the actual ray length instead of the capacity M."""
-        _lib.call("rn_max_count", _ptr(self.count), self.n_rays, _ptr(self._max_count_dev), current_stream_ptr())
-        self.launches += 1
-        self.max_count = max(1, int(self._max_count_dev.item()))
+        """Bin the rays by length class (one small device->host read of the class sizes, so
+        every class is launched with exactly the shared memory its rays need) and stage the
+        per-image camera centres for the depth pass."""
+        st = current_stream_ptr()
+        sizes = set(n for (_, n, _) in self.segments)
+        seg_len = sizes.pop() if len(sizes) == 1 else 0
+        _lib.call("rn_engine_bin_rays", self.params, _ptr(self.count), self.n_rays, int(seg_len), _ptr(self.order),
+                  _ptr(self._class_scratch), st)
+        self.launches += 2
+        cen = torch.stack([torch.cat([c.reshape(-1)[:3], c.new_ones(1)]) for (_, _, c) in self.segments]).contiguous()
+        self._centres = cen
+        self._seg_starts = torch.tensor([s for (s, _, _) in self.segments] + [self.n_rays], dtype=torch.int64,
+                                        device=self.dev)
+        sizes = self._class_scratch[:self.n_classes].cpu().numpy().astype(np.int64)     # the one sync
+        self.class_sizes = sizes
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        self._class_offsets = (ctypes.c_int64 * (self.n_classes + 1))(*[int(v) for v in off])
+        nz = np.nonzero(sizes[1:])[0]
+        self.max_count = int(min(self.M, 128 * (int(nz[-1]) + 1))) if len(nz) else 1
         return self.max_count
 
     # ------------------------------------------------------------------ BP
     def bp_iteration(self):
+        if self._class_offsets is None:
+            self.finalize_frontend()
         st = current_stream_ptr()
-        _lib.call("rn_fill_f32", _ptr(self.acc_new), sharding.seed_value(self.rank, self.prior), self.G, st)
+        _lib.call("rn_fill_f32", _ptr(self.acc_new), sharding.seed_value(self.rank, self.prior), self.GB, st)
         if self.sweep_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         _lib.call("rn_engine_bp_iteration", self.params, _ptr(self.hdr), _ptr(self.codes), _ptr(self.count),
-                  _ptr(self.s_hat), _ptr(self.msgs), _ptr(self.acc_prev), _ptr(self.acc_new),
-                  int(self.max_count), self.n_rays, st)
+                  _ptr(self.s_hat), _ptr(self.msgs), _ptr(self.acc_prev), _ptr(self.acc_new), _ptr(self.order),
+                  self._class_offsets, 1 if self.iterations_done == 0 else 0, int(self.max_count), self.n_rays, st)
         if self.sweep_events is not None:
             ev[1].record()
             self.sweep_events.append(ev)
-        self.launches += 2
+        self.launches += 1 + int(np.count_nonzero(self.class_sizes[1:]))
         if self.world > 1:
             sharding.allreduce_accumulator(self.acc_new, self.pg)
         self.acc_prev, self.acc_new = self.acc_new, self.acc_prev
@@ -156,23 +188,59 @@ class RayPotentialEngine(object):
             self.bp_iteration()
         return self.acc_prev
 
+    # ------------------------------------------------------------------ state access (row-major views)
+    def accumulator(self):
+        """acc_prev as the reference's row-major float32 [Gx, Gy, Gz] grid."""
+        out = torch.empty(self.grid_shape, dtype=torch.float32, device=self.dev)
+        _lib.call("rn_bricks_to_grid", self.params, _ptr(self.acc_prev), _ptr(out), 0, current_stream_ptr())
+        self.launches += 1
+        return out
+
+    def set_accumulator(self, grid):
+        """Load a row-major [Gx, Gy, Gz] grid (CUDA tensor or numpy) as acc_prev."""
+        if isinstance(grid, np.ndarray):
+            grid = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float32)).to(self.dev)
+        grid = grid.reshape(self.grid_shape).contiguous()
+        _lib.call("rn_grid_to_bricks", self.params, _ptr(grid), _ptr(self.acc_prev), self.prior, current_stream_ptr())
+        self.launches += 1
+
+    def set_messages(self, msgs):
+        """Load messages [n_rays, <= M] and mark the state as past the first sweep."""
+        if isinstance(msgs, np.ndarray):
+            msgs = torch.from_numpy(np.ascontiguousarray(msgs, dtype=np.float32)).to(self.dev)
+        self.msgs[:msgs.shape[0], :msgs.shape[1]].copy_(msgs)
+        self.iterations_done = max(self.iterations_done, 1)
+
+    def messages(self):
+        if self.iterations_done == 0:
+            return torch.zeros((self.n_rays, self.M), dtype=torch.float32, device=self.dev)
+        return self.msgs[:self.n_rays, :self.M]
+
     # ------------------------------------------------------------------ outputs
-    def depth(self, depth_out=None):
-        """Depth per ray (flat, ray order of add_image calls)."""
+    def depth(self, depth_out=None, S_new=None):
+        """Depth per ray (flat, ray order of add_image calls), all images in one launch."""
+        if self._class_offsets is None:
+            self.finalize_frontend()
         if depth_out is None:
             depth_out = torch.empty((self.n_rays,), dtype=torch.float32, device=self.dev)
-        st = current_stream_ptr()
-        for (start, n, centre) in self.segments:
-            sl = slice(start, start + n)
-            _lib.call("rn_engine_depth", self.params, _ptr(self.hdr[sl]), _ptr(self.codes[sl]), _ptr(self.count[sl]),
-                      _ptr(self.s_hat[sl]), _ptr(self.msgs[sl]), _ptr(self.acc_prev), _ptr(self.axes), _ptr(centre),
-                      _ptr(depth_out[sl]), int(self.max_count), n, st)
-            self.launches += 1
+        if self.iterations_done == 0:
+            self.msgs[:self.n_rays].zero_()
+        _lib.call("rn_engine_depth", self.params, _ptr(self.hdr), _ptr(self.codes), _ptr(self.count), _ptr(self.s_hat),
+                  _ptr(self.msgs), _ptr(self.acc_prev), _ptr(self.axes), _ptr(self._centres), _ptr(self._seg_starts),
+                  len(self.segments), _ptr(depth_out), _ptr(S_new), self.n_rays, current_stream_ptr())
+        self.launches += 1
         return depth_out
 
+    def depth_distribution(self):
+        """S_new [n_rays, M] (compute_depth_distribution, mrf_np.py:333-385) -- parity tests."""
+        S_new = torch.empty((self.n_rays, self.R), dtype=torch.float32, device=self.dev)
+        self.depth(S_new=S_new)
+        return S_new[:, :self.M]
+
     def occupancy(self):
-        out = torch.empty_like(self.acc_prev)
-        _lib.call("rn_occupancy", _ptr(self.acc_prev), _ptr(out), self.G, current_stream_ptr())
+        """sigmoid(acc_prev) as a row-major [Gx, Gy, Gz] grid (mrf_np.py:206-240)."""
+        out = torch.empty(self.grid_shape, dtype=torch.float32, device=self.dev)
+        _lib.call("rn_bricks_to_grid", self.params, _ptr(self.acc_prev), _ptr(out), 1, current_stream_ptr())
         self.launches += 1
         return out
 

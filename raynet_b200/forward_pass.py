@@ -221,8 +221,7 @@ class RayNetForwardPass(ForwardPass):
         gp = self._generation_params
         vg = scene.voxel_grid(gp.grid_shape)
         M = int(gp.max_number_of_marched_voxels)
-        M4 = (M + 3) // 4 * 4
-        eng = RayPotentialEngine(M4, gp.depth_planes, gp.neighbors + 1, F, scene.image_shape[0],
+        eng = RayPotentialEngine(M, gp.depth_planes, gp.neighbors + 1, F, scene.image_shape[0],
                                  scene.image_shape[1], gp.padding, scene.bbox.ravel(), vg.shape[1:],
                                  gamma=gp.gamma_mrf if gp.gamma_mrf is not None else 0.05,
                                  max_rays=n_rays_total)

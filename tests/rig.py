@@ -10,12 +10,14 @@ F = 32
 class Case(object):
     """One reference image of the synthetic ring rig with everything the kernels consume."""
 
-    def __init__(self, G, V, D, H, W, M, n_rays=None, ref_idx=0, seed=0, bbox=(-1, -1, -1, 1, 1, 1), grid=None):
+    def __init__(self, G, V, D, H, W, M, n_rays=None, ref_idx=0, seed=0, bbox=(-1, -1, -1, 1, 1, 1), grid=None,
+                 feature_scale=3.0):
         self.G, self.V, self.D, self.H, self.W, self.M = G, V, D, H, W, M
         self.grid = np.asarray(grid if grid is not None else (G, G, G), np.int32)
         self.bbox = np.asarray(bbox, np.float32)
         self.scene = SyntheticScene(V, H, W, self.grid, bbox=bbox)
-        self.features_all = random_features(V, H, W, F, PADDING, seed=seed)      # slot v = view v
+        # scaled up so that the plane softmax is peaked (scores ~ N(0, feature_scale^4 / F))
+        self.features_all = random_features(V, H, W, F, PADDING, seed=seed) * np.float32(feature_scale)
         self.vgrid = np.ascontiguousarray(get_voxel_grid(self.bbox, self.grid).transpose(1, 2, 3, 0))
         self.set_reference(ref_idx, n_rays, seed)
 
@@ -43,6 +45,11 @@ def case_c1(**kw):
 def case_small(**kw):
     """A 5-view / 32-plane case with rays long enough to span several 128-voxel chunks."""
     return Case(96, 5, 32, 48, 40, 288, n_rays=1200, **kw)
+
+
+def case_long(**kw):
+    """Rays of up to ~400 voxels (4 chunks of 128) on a 200^3 grid."""
+    return Case(200, 3, 16, 32, 32, 600, n_rays=600, **kw)
 
 
 def sigmoid(x):

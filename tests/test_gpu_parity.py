@@ -11,7 +11,7 @@ Gates (BASELINE.json north_star / SURVEY.md 8d):
 import numpy as np
 import pytest
 
-from rig import Case, case_c1, case_small, sigmoid
+from rig import Case, case_c1, case_long, case_small, sigmoid
 
 pytestmark = pytest.mark.gpu
 
@@ -33,8 +33,19 @@ def lib():
     return _lib
 
 
+_KEEP = []      # device tensors stay alive until the end of the test: raw data_ptr()s are handed to C
+
+
 def _d(torch, a):
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    _KEEP.append(t)
+    return t
+
+
+@pytest.fixture(autouse=True)
+def _release_device_tensors():
+    yield
+    del _KEEP[:]
 
 
 def _stream(torch):
@@ -232,7 +243,7 @@ def _random_state(c, o, seed=5):
     return acc, msgs
 
 
-@pytest.mark.parametrize("mk", [case_c1, case_small])
+@pytest.mark.parametrize("mk", [case_c1, case_small, case_long])
 def test_bp_single_sweep_vs_oracle(torch_cuda, lib, oracle, mk):
     """One synchronous sweep from identical state, reference layout (rn_bp_iteration) and
     resident layout (rn_engine_bp_iteration): messages and sigma(acc_new) within 1e-5 of the
@@ -248,15 +259,25 @@ def test_bp_single_sweep_vs_oracle(torch_cuda, lib, oracle, mk):
              _d(torch, o["cnt"]).data_ptr(), _d(torch, acc).data_ptr(), d_msgs.data_ptr(), d_acc_out.data_ptr(),
              c.N, _stream(torch))
     g_msgs, g_acc = d_msgs.cpu().numpy(), d_acc_out.cpu().numpy()
+    ref = {}
     for f64 in (False, True):
         dt = np.float64 if f64 else np.float32
         o_new = np.full(tuple(c.grid), PRIOR, dt)
         o_msgs = msgs.copy()
         oracle.bp_iteration(o["S_vox"], o["idx"], o["cnt"], c.grid, acc.astype(dt), o_new, o_msgs, acc_f64=f64)
-        assert np.abs(sigmoid(g_msgs) - sigmoid(o_msgs)).max() <= TOL_P
-        assert np.abs(sigmoid(g_acc) - sigmoid(o_new)).max() <= TOL_P
-        # log-odds themselves: loose absolute bound (they are not the gated quantity)
-        assert np.abs(g_msgs - o_msgs).max() < 5e-3
+        ref[f64] = (o_msgs, o_new)
+    # THE gate: the reference as it executes (mrf_np under NumPy >= 2: float64 occupancy chain)
+    assert np.abs(sigmoid(g_msgs) - sigmoid(ref[True][0])).max() <= TOL_P
+    assert np.abs(sigmoid(g_acc) - sigmoid(ref[True][1])).max() <= TOL_P
+    # the reference's float32 flavour (NumPy < 2, and its CUDA/TF backends) loses digits in
+    # 1 - o when o -> 1; the kernel (cancellation-free 1 - o) must be no further from it than
+    # that flavour is from the float64 one
+    flav = max(np.abs(sigmoid(ref[False][0]) - sigmoid(ref[True][0])).max(),
+               np.abs(sigmoid(ref[False][1]) - sigmoid(ref[True][1])).max())
+    assert np.abs(sigmoid(g_msgs) - sigmoid(ref[False][0])).max() <= max(TOL_P, 1.5 * flav)
+    assert np.abs(sigmoid(g_acc) - sigmoid(ref[False][1])).max() <= max(TOL_P, 1.5 * flav)
+    # log-odds themselves: loose absolute bound (they are not the gated quantity)
+    assert np.abs(g_msgs - ref[True][0]).max() < 5e-3
     # messages beyond count and rays with count <= 1 untouched
     for r in np.where(o["cnt"] <= 1)[0]:
         assert np.array_equal(g_msgs[r], msgs[r])
@@ -265,7 +286,7 @@ def test_bp_single_sweep_vs_oracle(torch_cuda, lib, oracle, mk):
     assert abs((g_acc.astype(np.float64) - PRIOR).sum() - g_msgs[valid].astype(np.float64).sum()) < 1e-2 * max(1, valid.sum() ** 0.5)
 
 
-@pytest.mark.parametrize("mk", [case_c1, case_small])
+@pytest.mark.parametrize("mk", [case_c1, case_small, case_long])
 def test_depth_estimate_vs_oracle(torch_cuda, lib, oracle, mk):
     torch = torch_cuda
     c = mk()
@@ -277,9 +298,10 @@ def test_depth_estimate_vs_oracle(torch_cuda, lib, oracle, mk):
              _d(torch, o["cnt"]).data_ptr(), _d(torch, acc).data_ptr(), _d(torch, msgs).data_ptr(),
              S_new.data_ptr(), c.N, _stream(torch))
     S_new = S_new.cpu().numpy()
-    for f64 in (False, True):
-        ref = oracle.depth_distribution(o["S_vox"], o["idx"], o["cnt"], c.grid, acc, msgs, acc_f64=f64)
-        assert np.abs(S_new - ref).max() <= TOL_P
+    ref64 = oracle.depth_distribution(o["S_vox"], o["idx"], o["cnt"], c.grid, acc, msgs, acc_f64=True)
+    ref32 = oracle.depth_distribution(o["S_vox"], o["idx"], o["cnt"], c.grid, acc, msgs, acc_f64=False)
+    assert np.abs(S_new - ref64).max() <= TOL_P
+    assert np.abs(S_new - ref32).max() <= max(TOL_P, 1.5 * np.abs(ref32 - ref64).max())
     occ = torch.zeros(tuple(c.grid), dtype=torch.float32, device="cuda")
     lib.call("rn_occupancy", _d(torch, acc).data_ptr(), occ.data_ptr(), acc.size, _stream(torch))
     assert np.abs(occ.cpu().numpy() - oracle.occupancy(acc)).max() <= 2e-7
@@ -355,16 +377,16 @@ def test_raynet_fp_and_de_vs_oracle(torch_cuda, oracle, mk):
     g_msgs = ret.get()
     assert np.array_equal(cnt.cpu().numpy(), o["cnt"]) and np.array_equal(idx.cpu().numpy(), o["idx"])
     assert np.abs(S_vox.cpu().numpy() - o["S_vox"]).max() <= TOL_P
-    o_new = np.full(tuple(c.grid), PRIOR, np.float32)
+    o_new = np.full(tuple(c.grid), PRIOR, np.float64)
     o_msgs = msgs.copy()
-    oracle.bp_iteration(o["S_vox"], o["idx"], o["cnt"], c.grid, acc, o_new, o_msgs)
+    oracle.bp_iteration(o["S_vox"], o["idx"], o["cnt"], c.grid, acc.astype(np.float64), o_new, o_msgs, acc_f64=True)
     assert np.abs(sigmoid(g_msgs) - sigmoid(o_msgs)).max() <= TOL_P
     assert np.abs(sigmoid(acc_out.cpu().numpy()) - sigmoid(o_new)).max() <= TOL_P
     # depth estimation closure
     depth = _d(torch, np.zeros((c.N,), np.float32))
     de(c.ray_idxs, c.features.ravel(), c.P.ravel(), c.P_inv.ravel(), c.centre, c.vgrid.ravel(), idx, cnt, S_vox,
        acc, msgs, depth)
-    ref_Snew = oracle.depth_distribution(o["S_vox"], o["idx"], o["cnt"], c.grid, acc, msgs)
+    ref_Snew = oracle.depth_distribution(o["S_vox"], o["idx"], o["cnt"], c.grid, acc, msgs, acc_f64=True)
     assert np.abs(S_vox.cpu().numpy() - ref_Snew).max() <= TOL_P
     ref_depth, ref_am = oracle.argmax_depth(ref_Snew, o["idx"], c.vgrid, c.grid, c.centre)
     _assert_depth_matches(depth.cpu().numpy(), ref_depth, ref_Snew)
@@ -400,7 +422,7 @@ def _run_engine(torch, c, iters, refs=None):
     return eng
 
 
-@pytest.mark.parametrize("mk,iters", [(case_c1, 3), (case_small, 3)])
+@pytest.mark.parametrize("mk,iters", [(case_c1, 3), (case_small, 3), (case_long, 2)])
 def test_engine_end_to_end_vs_oracle(torch_cuda, oracle, mk, iters):
     """C1 (and a longer-ray case) through the resident pipeline: every view a reference view in
     turn, I sweeps, depth pass -- against the oracle run the same way."""
@@ -419,18 +441,24 @@ def test_engine_end_to_end_vs_oracle(torch_cuda, oracle, mk, iters):
     assert np.array_equal(eng.count.cpu().numpy(), cnt)
     assert np.array_equal(eng.voxel_indices().cpu().numpy(), idx)
     g_occ = eng.occupancy().cpu().numpy()
-    worst = {}
+    occ = {}
     for f64 in (False, True):
         acc, msgs = oracle.belief_propagation(S_vox, idx, cnt, c.grid, gamma=0.05, bp_iterations=iters, acc_f64=f64)
-        worst[f64] = np.abs(g_occ - oracle.occupancy(acc)).max()
-    # multi-sweep gate: the reference's own two precision flavours differ by ~2e-5 here, so the
-    # kernel must be within 1e-5 of at least one flavour and within 5e-5 of both
-    assert min(worst.values()) <= TOL_P, worst
-    assert max(worst.values()) <= 5e-5, worst
+        occ[f64] = oracle.occupancy(acc)
+    # multi-sweep gate.  BP amplifies last-digit differences from sweep to sweep: the reference's
+    # own float32 flavour (its CUDA / TF backends, f32 accumulators) drifts `flav` away from its
+    # float64 flavour (NumPy >= 2).  The kernels accumulate in float32 (RED.ADD.F32), so they must
+    # stay within 1e-5 of the float64 reference or, where the reference disagrees with itself by
+    # more than that, within that disagreement.
+    flav = float(np.abs(occ[False] - occ[True]).max())
+    err = float(np.abs(g_occ - occ[True]).max())
+    print("end-to-end %d sweeps: |kernel - f64 ref| = %.2e, |f32 ref - f64 ref| = %.2e" % (iters, err, flav))
+    assert err <= max(TOL_P, 1.5 * flav), (err, flav)
     # depth pass from the engine's own final state vs oracle on that same state
-    g_acc = eng.acc_prev.cpu().numpy()
-    g_msgs = eng.msgs[:eng.n_rays].cpu().numpy()
-    ref_Snew = oracle.depth_distribution(S_vox, idx, cnt, c.grid, g_acc, g_msgs)
+    g_acc = eng.accumulator().cpu().numpy()
+    g_msgs = eng.messages().cpu().numpy()
+    ref_Snew = oracle.depth_distribution(S_vox, idx, cnt, c.grid, g_acc, g_msgs, acc_f64=True)
+    assert np.abs(eng.depth_distribution().cpu().numpy() - ref_Snew).max() <= TOL_P
     depth = eng.depth().cpu().numpy()
     n0 = 0
     for f, centre in fronts:
@@ -449,8 +477,8 @@ def test_engine_equals_reference_layout_path(torch_cuda, lib, oracle):
     o = _oracle_frontend(oracle, c)
     p = lib.make_params(M=c.M, grid_shape=c.grid)
     acc, msgs = _random_state(c, o, seed=2)
-    eng.msgs[:c.N].copy_(_d(torch, msgs))
-    eng.acc_prev.copy_(_d(torch, acc))
+    eng.set_messages(msgs)
+    eng.set_accumulator(acc)
     eng.bp_iteration()
     S_vox = torch.zeros((c.N, c.M), dtype=torch.float32, device="cuda")
     idx = torch.zeros((c.N, c.M, 3), dtype=torch.int32, device="cuda")
@@ -463,9 +491,9 @@ def test_engine_equals_reference_layout_path(torch_cuda, lib, oracle):
     acc_out = torch.full(tuple(c.grid), PRIOR, dtype=torch.float32, device="cuda")
     lib.call("rn_bp_iteration", p, S_vox.data_ptr(), idx.data_ptr(), cnt.data_ptr(), _d(torch, acc).data_ptr(),
              d_msgs.data_ptr(), acc_out.data_ptr(), c.N, _stream(torch))
-    a, b = eng.msgs[:c.N].cpu().numpy(), d_msgs.cpu().numpy()
+    a, b = eng.messages().cpu().numpy(), d_msgs.cpu().numpy()
     assert np.abs(sigmoid(a) - sigmoid(b)).max() <= 2e-6
-    assert np.abs(sigmoid(eng.acc_prev.cpu().numpy()) - sigmoid(acc_out.cpu().numpy())).max() <= 2e-6
+    assert np.abs(sigmoid(eng.accumulator().cpu().numpy()) - sigmoid(acc_out.cpu().numpy())).max() <= 2e-6
 
 
 def test_empty_and_degenerate_batches(torch_cuda, lib):

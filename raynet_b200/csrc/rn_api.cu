@@ -80,26 +80,6 @@ int make_dev(const RnParams *p, RnDev &d, bool need_grid, bool need_views, bool 
 
 inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
-inline int nch_for(int max_count) {
-    int n = (max_count + RN_CHUNK - 1) / RN_CHUNK;
-    if (n <= 1) return 1;
-    if (n <= 2) return 2;
-    if (n <= 4) return 4;
-    if (n <= 6) return 6;
-    if (n <= 8) return 8;
-    return -1;
-}
-
-#define RN_DISPATCH_NCH(nch, CALL)                                                             \
-    switch (nch) {                                                                             \
-        case 1: { constexpr int NCH = 1; CALL; } break;                                        \
-        case 2: { constexpr int NCH = 2; CALL; } break;                                        \
-        case 4: { constexpr int NCH = 4; CALL; } break;                                        \
-        case 6: { constexpr int NCH = 6; CALL; } break;                                        \
-        case 8: { constexpr int NCH = 8; CALL; } break;                                        \
-        default: return fail(RN_ERR_UNSUPPORTED, "rays longer than %d voxels are not supported", RN_MAX_NCH * RN_CHUNK); \
-    }
-
 int launch_dda(const RnDev &d, const DdaArgs &a, cudaStream_t st) {
     if (a.n_rays <= 0) return RN_OK;
     const int threads = 128;
@@ -116,28 +96,30 @@ int launch_dda_codes(const RnDev &d, const DdaCodesArgs &a, cudaStream_t st) {
     return check_launch("dda_codes_kernel");
 }
 
-template <int NCH, bool kAos>
-int launch_simmap_t(const RnDev &d, const SimMapArgs &a, cudaStream_t st) {
+// tiled enumeration of ray positions: whole columns of whole 8x8 tiles only (rn_tiled_position)
+inline int64_t tile_len_for(const RnDev &d, int64_t n_rays) {
+    const int H = d.H;
+    if (H <= 0 || (H % 8) != 0 || (n_rays % H) != 0 || ((n_rays / H) % 8) != 0) return 0;
+    return n_rays;
+}
+
+template <bool kAos>
+int launch_simmap(const RnDev &d, SimMapArgs a, bool mapping, cudaStream_t st) {
+    if (a.n_rays <= 0) return RN_OK;
     const int warps = 4;
-    const size_t smem = rn_simmap_smem_bytes(d.D, d.V, warps);
+    if (!mapping) a.count = nullptr;
+    a.val_stride = mapping ? (int)row_stride_of(d.M) : 0;
+    a.tile_len = tile_len_for(d, a.n_rays);
+    const size_t smem = rn_simmap_smem_bytes(d.D, d.V, a.val_stride, warps);
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(simmap_kernel<NCH, kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(simmap_kernel<kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(RN_ERR_CUDA, "simmap smem attribute: %s", cudaGetErrorString(e));
         configured = smem;
     }
     const int64_t blocks = (a.n_rays + warps - 1) / warps;
-    simmap_kernel<NCH, kAos><<<(unsigned)blocks, warps * 32, smem, st>>>(d, a);
+    simmap_kernel<kAos><<<(unsigned)blocks, warps * 32, smem, st>>>(d, a);
     return check_launch("simmap_kernel");
-}
-
-template <bool kAos>
-int launch_simmap(const RnDev &d, const SimMapArgs &a, int max_count, bool mapping, cudaStream_t st) {
-    if (a.n_rays <= 0) return RN_OK;
-    if (!mapping) return launch_simmap_t<0, kAos>(d, a, st);
-    int nch = nch_for(max_count);
-    RN_DISPATCH_NCH(nch, return (launch_simmap_t<NCH, kAos>(d, a, st)));
-    return RN_OK;
 }
 
 // One BP sweep over rays [a.first, a.first + a.n) of a.order (or of the ray array itself).
@@ -183,6 +165,26 @@ struct AxisScratch {
     int cap = 0;
 };
 thread_local AxisScratch g_axes;
+
+// Scratch for the ray start / end points handed from the DDA kernel to the similarity kernel
+// when the caller does not ask for them.
+struct RayScratch {
+    float *ptr = nullptr;
+    int64_t cap = 0;
+};
+thread_local RayScratch g_rays;
+
+int ray_scratch(int64_t n_rays, float **starts, float **ends) {
+    if (g_rays.cap < n_rays) {
+        if (g_rays.ptr) cudaFree(g_rays.ptr);
+        cudaError_t e = cudaMalloc(&g_rays.ptr, sizeof(float) * 6 * (size_t)n_rays);
+        if (e != cudaSuccess) { g_rays.ptr = nullptr; g_rays.cap = 0; return fail(RN_ERR_CUDA, "cudaMalloc ray scratch: %s", cudaGetErrorString(e)); }
+        g_rays.cap = n_rays;
+    }
+    *starts = g_rays.ptr;
+    *ends = g_rays.ptr + 3 * n_rays;
+    return RN_OK;
+}
 
 int axes_from_voxel_grid(const RnDev &d, const float *voxel_grid, float **axes, cudaStream_t st) {
     const int n = d.gx + d.gy + d.gz;
@@ -249,7 +251,7 @@ int rn_similarity(const RnParams *p, const float *features, const float *P, cons
     if (rc) return rc;
     SimMapArgs a = {};
     a.features = features; a.P = P; a.starts_in = starts; a.ends_in = ends; a.S_planes = S_out; a.n_rays = n_rays;
-    return launch_simmap<true>(d, a, 0, false, S(stream));
+    return launch_simmap<true>(d, a, false, S(stream));
 }
 
 int rn_mvcnn_forward(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
@@ -260,7 +262,7 @@ int rn_mvcnn_forward(const RnParams *p, const int32_t *ray_idxs, const float *fe
     SimMapArgs a = {};
     a.ray_idxs = ray_idxs; a.features = features; a.P = P; a.P_inv = P_inv; a.centre = centre;
     a.S_planes = S_out; a.n_rays = n_rays;
-    return launch_simmap<true>(d, a, 0, false, S(stream));
+    return launch_simmap<true>(d, a, false, S(stream));
 }
 
 int rn_mvcnn_forward_depth(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
@@ -272,7 +274,7 @@ int rn_mvcnn_forward_depth(const RnParams *p, const int32_t *ray_idxs, const flo
     SimMapArgs a = {};
     a.ray_idxs = ray_idxs; a.features = features; a.P = P; a.P_inv = P_inv; a.centre = centre;
     a.S_planes = S_out; a.points = points; a.depth_planes = depth_map; a.n_rays = n_rays;
-    return launch_simmap<true>(d, a, 0, false, S(stream));
+    return launch_simmap<true>(d, a, false, S(stream));
 }
 
 int rn_voxel_traversal(const RnParams *p, const float *starts, const float *ends, int32_t *ray_voxel_indices,
@@ -368,16 +370,20 @@ static int frontend_ref_layout(const RnDev &d, const int32_t *ray_idxs, const fl
                                const float *P_inv, const float *centre, const float *axes,
                                int32_t *ray_voxel_indices, int32_t *ray_voxel_count, float *S_vox,
                                float *depth_vox, int64_t n_rays, cudaStream_t st) {
+    float *starts = nullptr, *ends = nullptr;
+    int rc = ray_scratch(n_rays, &starts, &ends);
+    if (rc) return rc;
     DdaArgs da = {};
-    da.ray_idxs = ray_idxs; da.P_inv = P_inv; da.centre = centre;
+    da.ray_idxs = ray_idxs; da.P_inv = P_inv; da.centre = centre; da.starts = starts; da.ends = ends;
     da.idx = ray_voxel_indices; da.count = ray_voxel_count; da.n_rays = n_rays;
-    int rc = launch_dda(d, da, st);
+    rc = launch_dda(d, da, st);
     if (rc) return rc;
     SimMapArgs a = {};
+    a.starts_in = starts; a.ends_in = ends;
     a.ray_idxs = ray_idxs; a.features = features; a.P = P; a.P_inv = P_inv; a.centre = centre;
     a.axes = axes; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.S_vox = S_vox; a.depth_vox = depth_vox;
     a.n_rays = n_rays;
-    return launch_simmap<true>(d, a, d.M, true, st);
+    return launch_simmap<true>(d, a, true, st);
 }
 
 int rn_raynet_fp(const RnParams *p, const int32_t *ray_idxs, const float *features, const float *P,
@@ -492,15 +498,20 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
             return fail(RN_ERR_UNSUPPORTED, "feature volume too large for int32 element offsets");
     }
     if ((starts == nullptr) != (ends == nullptr)) return fail(RN_ERR_SHAPE, "starts and ends must both be given or both NULL");
+    if (!starts) {
+        rc = ray_scratch(n_rays, &starts, &ends);
+        if (rc) return rc;
+    }
     DdaCodesArgs da = {};
     da.ray_idxs = ray_idxs; da.P_inv = P_inv; da.centre = centre; da.starts = starts; da.ends = ends;
     da.hdr = ray_hdr; da.codes = codes; da.count = count; da.n_rays = n_rays;
     rc = launch_dda_codes(d, da, S(stream));
     if (rc) return rc;
     SimMapArgs a = {};
+    a.starts_in = starts; a.ends_in = ends;
     a.ray_idxs = ray_idxs; a.features = features; a.view_ids = view_ids; a.P = P; a.P_inv = P_inv; a.centre = centre;
     a.axes = axis_centres; a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.n_rays = n_rays;
-    return launch_simmap<false>(d, a, d.M, true, S(stream));
+    return launch_simmap<false>(d, a, true, S(stream));
 }
 
 int rn_engine_bin_rays(const RnParams *p, const int32_t *count, int64_t n_rays, int64_t seg_len, int32_t *order,

@@ -120,11 +120,11 @@ struct SimMapArgs {
     const int32_t *ray_idxs;   // non-null: rays start from sample_in_bbox; null: starts/ends are inputs
     const float *features, *P, *P_inv, *centre;
     const int32_t *view_ids;   // optional [V]: slot of each view inside `features` (null = 0..V-1)
-    const float *starts_in, *ends_in;
+    const float *starts_in, *ends_in;   // optional [n][3]: precomputed sample_in_bbox results (same arithmetic)
     float *S_planes;           // [n][D]     optional out
     float *points;             // [n][D][4]  optional out
     float *depth_planes;       // [n]        optional out: |point[argmax_k S] - C|
-    // mapping stage (NCH > 0)
+    // mapping stage (count != null)
     const float *axes;         // [Gx+Gy+Gz] voxel-centre coordinates per axis
     const int32_t *idx;        // kAos
     const uint32_t *hdr;       // !kAos
@@ -134,53 +134,68 @@ struct SimMapArgs {
     float *s_hat;              // [n][row_stride] optional out: clip_and_renorm(S_voxel_space)
     float *depth_vox;          // [n] optional out: |centre(argmax voxel of S_vox) - C|
     int64_t n_rays;
+    int64_t tile_len;          // > 0: warps walk the rays in 8x8-pixel tiles (rn_tiled_position)
+    int val_stride;            // floats of the per-warp voxel buffer (0 without mapping stage)
 };
 
-// dynamic shared memory per CTA: [V*12 P][12 P_inv][4 C][V view slots] + per warp [D*V offsets][D S]
-__host__ __device__ inline size_t rn_simmap_smem_bytes(int D, int V, int warps) {
-    return sizeof(float) * (size_t)(V * 12 + 16 + V) + (size_t)warps * (sizeof(int) * (size_t)D * V + sizeof(float) * (size_t)D);
+// dynamic shared memory: per CTA [V*12 P][12 P_inv][4 C][V view slots], per warp
+// [D*V feature offsets][D plane scores][val_stride voxel values]
+__host__ __device__ inline size_t rn_simmap_smem_bytes(int D, int V, int val_stride, int warps) {
+    return sizeof(float) * (size_t)(V * 12 + 16 + ((V + 3) & ~3)) +
+           (size_t)warps * sizeof(float) * ((size_t)((D * V + 3) & ~3) + (size_t)((D + 3) & ~3) + (size_t)val_stride);
 }
 
-template <int NCH, bool kAos>
+// One warp per ray.
+//  (1) every (plane, view) sample of the ray is projected by one lane (reference arithmetic,
+//      IEEE division: the rounded pixel must equal the oracle's) -> feature offsets in smem;
+//  (2) plane scores: S_k = sum_{i<j} <f_i, f_j> = 1/2 (|sum_v f_v|^2 - sum_v |f_v|^2).  For F = 32
+//      a lane owns 4 channels (one LDG.128) and 8 lanes cover a feature vector, so one warp
+//      instruction fetches the vectors of 4 planes; other F fall back to lane = channel;
+//  (3) softmax over planes;  (4) plane -> voxel interpolation with the voxel values parked in
+//      shared memory between the three passes (sum, clip + renormalise, store).
+template <bool kAos>
 __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warps = blockDim.x >> 5;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = p.D, V = p.V, DV = p.D * p.V;
     float *sP = reinterpret_cast<float *>(smem_raw);
-    float *sPinv = sP + p.V * 12;
+    float *sPinv = sP + V * 12;
     float *sC = sPinv + 12;
     int *sView = reinterpret_cast<int *>(sC + 4);
-    int *sOffAll = sView + p.V;
-    int *sOff = sOffAll + (size_t)wid * p.D * p.V;
-    float *sS = reinterpret_cast<float *>(sOffAll + (size_t)warps * p.D * p.V) + (size_t)wid * p.D;
+    float *warp0 = reinterpret_cast<float *>(sView + ((V + 3) & ~3));
+    const size_t per_warp = (size_t)((DV + 3) & ~3) + (size_t)((D + 3) & ~3) + (size_t)a.val_stride;
+    int *sOff = reinterpret_cast<int *>(warp0 + (size_t)wid * per_warp);
+    float *sS = reinterpret_cast<float *>(sOff + ((DV + 3) & ~3));
+    float *sVal = sS + ((D + 3) & ~3);
 
-    for (int i = threadIdx.x; i < p.V * 12; i += blockDim.x) sP[i] = __ldg(a.P + i);
+    for (int i = threadIdx.x; i < V * 12; i += blockDim.x) sP[i] = __ldg(a.P + i);
     if (threadIdx.x < 12) sPinv[threadIdx.x] = a.P_inv ? __ldg(a.P_inv + threadIdx.x) : 0.f;
     if (threadIdx.x < 3) sC[threadIdx.x] = a.centre ? __ldg(a.centre + threadIdx.x) : 0.f;
-    if (threadIdx.x < p.V) sView[threadIdx.x] = a.view_ids ? __ldg(a.view_ids + threadIdx.x) : (int)threadIdx.x;
+    if (threadIdx.x < V) sView[threadIdx.x] = a.view_ids ? __ldg(a.view_ids + threadIdx.x) : (int)threadIdx.x;
     __syncthreads();
 
-    const int64_t r = (int64_t)blockIdx.x * warps + wid;
-    if (r >= a.n_rays) return;
+    const int64_t t = (int64_t)blockIdx.x * warps + wid;
+    if (t >= a.n_rays) return;
+    const int64_t r = rn_tiled_position(t, a.tile_len, p.H);
 
     // ---- a1: ray start / end -------------------------------------------------------
     float rs[3], re[3];
-    if (a.ray_idxs) {
-        rn_sample_in_bbox(__ldg(a.ray_idxs + r), p, sPinv, sC, rs, re);
-    } else {
+    if (a.starts_in) {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             rs[i] = __ldg(a.starts_in + 3 * r + i);
             re[i] = __ldg(a.ends_in + 3 * r + i);
         }
+    } else {
+        rn_sample_in_bbox(__ldg(a.ray_idxs + r), p, sPinv, sC, rs, re);
     }
 
-    // ---- a2 step A: project every (plane, view) sample, one sample per lane ----------
-    const int D = p.D, V = p.V, DV = p.D * p.V;
+    // ---- a2 step 1: project every (plane, view) sample, one sample per lane ----------
     for (int s0 = 0; s0 < DV; s0 += 32) {
-        int sidx = s0 + lane;
+        const int sidx = s0 + lane;
         if (sidx < DV) {
-            int k = sidx / V, v = sidx - k * V;
+            const int k = sidx / V, v = sidx - k * V;
             float pt[3];
 #pragma unroll
             for (int i = 0; i < 3; i++) pt[i] = rs[i] + (float)k * (re[i] - rs[i]) / (float)(D - 1);
@@ -189,72 +204,67 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
     }
     __syncwarp();
 
-    // ---- a2 step B: S_k = sum_{i<j} <f_i, f_j> = 1/2 (|sum_v f_v|^2 - sum_v |f_v|^2) ------
-    // lane = feature channel; 32 planes per block are reduced across lanes with a
-    // 31-shuffle transpose-reduce so that lane l ends up with plane (kb*32 + l).
-    const int DPL = (D + 31) >> 5;   // planes per lane
-    float Sval[4];                   // D <= 128
-#pragma unroll
-    for (int kb = 0; kb < 4; kb++) {
-        Sval[kb] = -INFINITY;
-        if (kb < DPL) {
-            float part[32];
-#pragma unroll
-            for (int kk = 0; kk < 32; kk++) part[kk] = 0.f;
+    // ---- a2 step 2: plane scores --------------------------------------------------------
+    const float inv_pairs = 0.5f / (float)p.npairs;
+    if (p.F == 32) {
+        const int g = lane >> 3, cl = (lane & 7) * 4;
+        for (int k0 = 0; k0 < D; k0 += 4) {
+            const int k = min(k0 + g, D - 1);
+            const int *offk = sOff + k * V;
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            float sq = 0.f;
+#pragma unroll 3
+            for (int v = 0; v < V; v++) {
+                const float4 f = __ldg(reinterpret_cast<const float4 *>(a.features + (int64_t)offk[v] + cl));
+                sum.x += f.x; sum.y += f.y; sum.z += f.z; sum.w += f.w;
+                sq = fmaf(f.x, f.x, sq); sq = fmaf(f.y, f.y, sq); sq = fmaf(f.z, f.z, sq); sq = fmaf(f.w, f.w, sq);
+            }
+            float val = fmaf(sum.x, sum.x, fmaf(sum.y, sum.y, fmaf(sum.z, sum.z, fmaf(sum.w, sum.w, -sq))));
+            val += __shfl_xor_sync(RN_FULL_MASK, val, 1);
+            val += __shfl_xor_sync(RN_FULL_MASK, val, 2);
+            val += __shfl_xor_sync(RN_FULL_MASK, val, 4);
+            if ((lane & 7) == 0 && k0 + g < D) sS[k0 + g] = val * inv_pairs;
+        }
+    } else {   // any F: lane = channel (strided), one warp reduction per plane
+        for (int k = 0; k < D; k++) {
+            const int *offk = sOff + k * V;
+            float part = 0.f;
             for (int c0 = 0; c0 < p.F; c0 += 32) {
                 const int ch = c0 + lane;
-                const bool chok = ch < p.F;
-#pragma unroll
-                for (int kk = 0; kk < 32; kk++) {
-                    const int k = kb * 32 + kk;
-                    if (k < D) {
-                        float sum = 0.f, sq = 0.f;
-                        const int *offk = sOff + k * V;
-                        for (int v = 0; v < V; v++) {
-                            float f = chok ? __ldg(a.features + (int64_t)offk[v] + ch) : 0.f;
-                            sum += f;
-                            sq = fmaf(f, f, sq);
-                        }
-                        part[kk] += fmaf(sum, sum, -sq);
+                float sum = 0.f, sq = 0.f;
+                if (ch < p.F) {
+                    for (int v = 0; v < V; v++) {
+                        const float f = __ldg(a.features + (int64_t)offk[v] + ch);
+                        sum += f;
+                        sq = fmaf(f, f, sq);
                     }
                 }
+                part += fmaf(sum, sum, -sq);
             }
-#pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) {
-                const bool upper = (lane & s) != 0;
-#pragma unroll
-                for (int i = 0; i < s; i++) {
-                    float send = upper ? part[i] : part[i + s];
-                    float keep = upper ? part[i + s] : part[i];
-                    part[i] = keep + __shfl_xor_sync(RN_FULL_MASK, send, s);
-                }
-            }
-            const int k = kb * 32 + lane;
-            if (k < D) Sval[kb] = (0.5f * part[0]) / (float)p.npairs;
+            part = rn_warp_sum(part);
+            if (lane == 0) sS[k] = part * inv_pairs;
         }
     }
+    __syncwarp();
+
     // ---- softmax over the D planes (feature_similarities.cu:109-123) -------------------
     float mx = -INFINITY;
-#pragma unroll
-    for (int kb = 0; kb < 4; kb++) mx = fmaxf(mx, Sval[kb]);
+    for (int k = lane; k < D; k += 32) mx = fmaxf(mx, sS[k]);
     mx = rn_warp_max(mx);
     float ssum = 0.f;
-#pragma unroll
-    for (int kb = 0; kb < 4; kb++) {
-        const int k = kb * 32 + lane;
-        Sval[kb] = (kb < DPL && k < D) ? expf(Sval[kb] - mx) : 0.f;
-        ssum += Sval[kb];
+    for (int k = lane; k < D; k += 32) {
+        const float ev = expf(sS[k] - mx);
+        sS[k] = ev;
+        ssum += ev;
     }
     ssum = rn_warp_sum(ssum);
-#pragma unroll
-    for (int kb = 0; kb < 4; kb++) {
-        const int k = kb * 32 + lane;
-        if (kb < DPL && k < D) {
-            float v = Sval[kb] / ssum;
-            Sval[kb] = v;
-            sS[k] = v;
-            if (a.S_planes) a.S_planes[r * (int64_t)D + k] = v;
-        }
+    float bv = -INFINITY;   // first arg-max over planes (similarities.py:213-229)
+    int bk = 0;
+    for (int k = lane; k < D; k += 32) {
+        const float v = sS[k] / ssum;
+        sS[k] = v;
+        if (a.S_planes) a.S_planes[r * (int64_t)D + k] = v;
+        if (v > bv) { bv = v; bk = k; }
     }
     __syncwarp();
 
@@ -268,14 +278,7 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
             reinterpret_cast<float4 *>(a.points)[r * (int64_t)D + k] = q;
         }
     }
-    if (a.depth_planes) {   // similarities.py:213-229: first arg-max over planes
-        float bv = -INFINITY;
-        int bk = 0;
-#pragma unroll
-        for (int kb = 0; kb < 4; kb++) {
-            const int k = kb * 32 + lane;
-            if (kb < DPL && k < D && Sval[kb] > bv) { bv = Sval[kb]; bk = k; }
-        }
+    if (a.depth_planes) {
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
             float ov = __shfl_xor_sync(RN_FULL_MASK, bv, d);
@@ -295,134 +298,121 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
     }
 
     // ---- a4: plane -> voxel mapping (planes_voxels_mapping.cu:6-92) ---------------------
-    if constexpr (NCH > 0) {
-        const int L = __ldg(a.count + r);
-        if (L <= 0) {
-            if (a.depth_vox && lane == 0) {
-                // raynet/mvcnn depth kernels read slot 0 of a zero-filled list: voxel (0,0,0)
-                float sum = 0.f;
-                float cc[3] = {__ldg(a.axes), __ldg(a.axes + p.gx), __ldg(a.axes + p.gx + p.gy)};
+    if (a.count == nullptr) return;
+    const int L = __ldg(a.count + r);
+    if (L <= 0) {
+        if (a.depth_vox && lane == 0) {
+            // raynet/mvcnn depth kernels read slot 0 of a zero-filled list: voxel (0,0,0)
+            float sum = 0.f;
+            float cc[3] = {__ldg(a.axes), __ldg(a.axes + p.gx), __ldg(a.axes + p.gx + p.gy)};
 #pragma unroll
-                for (int i = 0; i < 3; i++) { float dd = cc[i] - sC[i]; sum += dd * dd; }
-                a.depth_vox[r] = sqrtf(sum);
-            }
-            return;
+            for (int i = 0; i < 3; i++) { float dd = cc[i] - sC[i]; sum += dd * dd; }
+            a.depth_vox[r] = sqrtf(sum);
         }
-        const int nch = (L + RN_CHUNK - 1) / RN_CHUNK;
-        float ray[3];
+        return;
+    }
+    const int nch = (L + RN_CHUNK - 1) / RN_CHUNK;
+    float ray[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++) ray[i] = re[i] - rs[i];
-        float ray_norm = 0.f;
+    for (int i = 0; i < 3; i++) ray[i] = re[i] - rs[i];
+    float ray_norm = 0.f;
 #pragma unroll
-        for (int i = 0; i < 3; i++) ray_norm += ray[i] * ray[i];
-        const float pstep = (1.0f - 0.0f) / (float)(D - 1);
+    for (int i = 0; i < 3; i++) ray_norm += ray[i] * ray[i];
+    const float pstep = (1.0f - 0.0f) / (float)(D - 1);
+    const float fDm1 = (float)(D - 1);
 
-        // voxel (c, j) of this lane = c*128 + 32*j + lane: lanes walk CONSECUTIVE voxels, so the
-        // row stores below are plain coalesced 128-byte warp stores and the step codes decode
-        // with popc (rn_engine.cuh)
-        RayHead head = {0, 0, 0, 1, 1, 1};
-        const uint2 *words = nullptr;
-        const int32_t *idx_row = nullptr;
+    // voxel (c, j) of this lane = c*128 + 32*j + lane: lanes walk CONSECUTIVE voxels; the step
+    // codes decode with popc (rn_engine.cuh)
+    RayHead head = {0, 0, 0, 1, 1, 1};
+    const uint2 *words = nullptr;
+    const int32_t *idx_row = nullptr;
+    if (kAos) {
+        idx_row = a.idx + r * (int64_t)p.M * 3;
+    } else {
+        head = rn_ray_head(a.hdr + 2 * r);
+        words = reinterpret_cast<const uint2 *>(a.codes + r * (int64_t)p.code_stride);
+    }
+    StepCount before = {0, 0, 0};
+    float lsum = 0.f;
+    float bestv = -INFINITY;
+    int besti = 0, bestx = 0, besty = 0, bestz = 0;
+    for (int c = 0; c < nch; c++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = c * RN_CHUNK + 32 * j + lane;
+            int vx = 0, vy = 0, vz = 0;
+            if (kAos) {
+                if (i < L) { vx = __ldg(idx_row + 3 * i); vy = __ldg(idx_row + 3 * i + 1); vz = __ldg(idx_row + 3 * i + 2); }
+            } else {
+                const uint2 cw = __ldg(words + c * 4 + j);
+                rn_decode_pair(head, cw.x, cw.y, lane, before, vx, vy, vz);
+            }
+            if (i < L) {
+                float cc[3] = {__ldg(a.axes + vx), __ldg(a.axes + p.gx + vy), __ldg(a.axes + p.gx + p.gy + vz)};
+                float sum = 0.f;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    float vd = cc[q];
+                    vd -= rs[q];
+                    sum += ray[q] * vd;
+                }
+                const float tt = rn_clampf(sum / ray_norm, 1e-4f, 1 - 1e-4f);
+                // stateless form of the reference's persistent two-pointer bracket: the smallest
+                // left with t - (left+1)*step <= 0, searched upwards from a safe lower bound
+                int left = max(0, (int)(tt * fDm1) - 2);
+                while (tt - (0.0f + (float)(left + 1) * pstep) > 0 && tt - (0.0f + (float)left * pstep) > 0) left++;
+                const float left_d = fabsf(tt - (0.0f + (float)left * pstep));
+                const float right_d = fabsf(tt - (0.0f + (float)(left + 1) * pstep));
+                // 1 - l/(l+r) = r/(l+r) and 1 - r/(l+r) = l/(l+r)
+                const float inv = 1.0f / (left_d + right_d);
+                const float out = (right_d * inv) * sS[left] + (left_d * inv) * sS[left + 1];
+                sVal[i] = out;
+                lsum += out;
+                if (out > bestv) { bestv = out; besti = i; bestx = vx; besty = vy; bestz = vz; }
+            }
+        }
+    }
+    const float inv_sr = 1.0f / rn_warp_sum(lsum);
+    __syncwarp();
+    // normalise; clip + renormalise (mrf_np.py:4-8)
+    float csum = 0.f;
+    for (int i = lane; i < L; i += 32) {
+        float v = sVal[i] * inv_sr;
+        if (a.S_vox) a.S_vox[r * (int64_t)p.row_stride + i] = v;
+        v = rn_clampf(v, 1e-5f, 0.99999f);
+        sVal[i] = v;
+        csum += v;
+    }
+    if (a.s_hat) {
+        const float inv_c = 1.0f / rn_warp_sum(csum);
+        __syncwarp();
+        float *out_row = a.s_hat + r * (int64_t)p.row_stride;
         if (kAos) {
-            idx_row = a.idx + r * (int64_t)p.M * 3;
-        } else {
-            head = rn_ray_head(a.hdr + 2 * r);
-            words = reinterpret_cast<const uint2 *>(a.codes + r * (int64_t)p.code_stride);
-        }
-        StepCount before = {0, 0, 0};
-
-        float val[NCH][4];
-        float lsum = 0.f;
-        float bestv = -INFINITY;
-        int besti = 0, bestx = 0, besty = 0, bestz = 0;
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            if (c < nch) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int i = c * RN_CHUNK + 32 * j + lane;
-                    int vx = 0, vy = 0, vz = 0;
-                    if (kAos) {
-                        if (i < L) { vx = __ldg(idx_row + 3 * i); vy = __ldg(idx_row + 3 * i + 1); vz = __ldg(idx_row + 3 * i + 2); }
-                    } else {
-                        const uint2 cw = __ldg(words + c * 4 + j);
-                        rn_decode_pair(head, cw.x, cw.y, lane, before, vx, vy, vz);
-                    }
-                    float out = 0.f;
-                    if (i < L) {
-                        float cc[3] = {__ldg(a.axes + vx), __ldg(a.axes + p.gx + vy), __ldg(a.axes + p.gx + p.gy + vz)};
-                        float sum = 0.f;
-#pragma unroll
-                        for (int t = 0; t < 3; t++) {
-                            float vd = cc[t];
-                            vd -= rs[t];
-                            sum += ray[t] * vd;
-                        }
-                        float t = rn_clampf(sum / ray_norm, 1e-4f, 1 - 1e-4f);
-                        // stateless form of the reference's persistent two-pointer bracket:
-                        // smallest left with t - (left+1)*step <= 0
-                        int left = max(0, (int)floorf(t / pstep) - 2);
-                        while (t - (0.0f + (float)(left + 1) * pstep) > 0 && t - (0.0f + (float)left * pstep) > 0)
-                            left++;
-                        float left_d = fabsf(t - (0.0f + (float)left * pstep));
-                        float right_d = fabsf(t - (0.0f + (float)(left + 1) * pstep));
-                        float c1 = (float)(1.0 - (double)(left_d / (left_d + right_d)));
-                        float c2 = (float)(1.0 - (double)(right_d / (left_d + right_d)));
-                        out = c1 * sS[left] + c2 * sS[left + 1];
-                        if (out > bestv) { bestv = out; besti = i; bestx = vx; besty = vy; bestz = vz; }
-                    }
-                    val[c][j] = out;
-                    lsum += out;
-                }
+            for (int i = lane; i < L; i += 32) out_row[i] = sVal[i] * inv_c;
+        } else {   // resident rows are 16-byte aligned and padded to whole chunks
+            for (int i = 4 * lane; i < L; i += 128) {
+                float4 v = *reinterpret_cast<const float4 *>(sVal + i);
+                v.x *= inv_c; v.y *= inv_c; v.z *= inv_c; v.w *= inv_c;
+                rn_st_stream4(out_row + i, v);
             }
         }
-        const float srsum = rn_warp_sum(lsum);
-        // normalise; optionally clip + renormalise (mrf_np.py:4-8)
-        float csum = 0.f;
+    }
+    if (a.depth_vox) {   // mvcnn_with_ray_marching...py:280-312: first arg-max over the M slots
 #pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            if (c < nch) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int i = c * RN_CHUNK + 32 * j + lane;
-                    float v = val[c][j] / srsum;
-                    if (a.S_vox && i < L) a.S_vox[r * (int64_t)p.row_stride + i] = v;
-                    v = (i < L) ? rn_clampf(v, 1e-5f, 0.99999f) : 0.f;
-                    val[c][j] = v;
-                    csum += v;
-                }
-            }
+        for (int d = 16; d >= 1; d >>= 1) {
+            float ov = __shfl_xor_sync(RN_FULL_MASK, bestv, d);
+            int oi = __shfl_xor_sync(RN_FULL_MASK, besti, d);
+            int ox = __shfl_xor_sync(RN_FULL_MASK, bestx, d);
+            int oy = __shfl_xor_sync(RN_FULL_MASK, besty, d);
+            int oz = __shfl_xor_sync(RN_FULL_MASK, bestz, d);
+            if (ov > bestv || (ov == bestv && oi < besti)) { bestv = ov; besti = oi; bestx = ox; besty = oy; bestz = oz; }
         }
-        if (a.s_hat) {
-            csum = rn_warp_sum(csum);
+        if (lane == 0) {
+            float cc[3] = {__ldg(a.axes + bestx), __ldg(a.axes + p.gx + besty), __ldg(a.axes + p.gx + p.gy + bestz)};
+            float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                if (c < nch) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int i = c * RN_CHUNK + 32 * j + lane;
-                        if (i < L) a.s_hat[r * (int64_t)p.row_stride + i] = val[c][j] / csum;
-                    }
-                }
-            }
-        }
-        if (a.depth_vox) {   // mvcnn_with_ray_marching...py:280-312: first arg-max over the M slots
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                float ov = __shfl_xor_sync(RN_FULL_MASK, bestv, d);
-                int oi = __shfl_xor_sync(RN_FULL_MASK, besti, d);
-                int ox = __shfl_xor_sync(RN_FULL_MASK, bestx, d);
-                int oy = __shfl_xor_sync(RN_FULL_MASK, besty, d);
-                int oz = __shfl_xor_sync(RN_FULL_MASK, bestz, d);
-                if (ov > bestv || (ov == bestv && oi < besti)) { bestv = ov; besti = oi; bestx = ox; besty = oy; bestz = oz; }
-            }
-            if (lane == 0) {
-                float cc[3] = {__ldg(a.axes + bestx), __ldg(a.axes + p.gx + besty), __ldg(a.axes + p.gx + p.gy + bestz)};
-                float sum = 0.f;
-#pragma unroll
-                for (int i = 0; i < 3; i++) { float dd = cc[i] - sC[i]; sum += dd * dd; }
-                a.depth_vox[r] = sqrtf(sum);
-            }
+            for (int i = 0; i < 3; i++) { float dd = cc[i] - sC[i]; sum += dd * dd; }
+            a.depth_vox[r] = sqrtf(sum);
         }
     }
 }

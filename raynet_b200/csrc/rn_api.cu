@@ -130,14 +130,14 @@ int launch_bp2(const RnDev &d, Bp2Args a, bool first_sweep, int nch_max, cudaStr
         return fail(RN_ERR_UNSUPPORTED, "rays longer than %d voxels are not supported", RN_MAX_NCH * RN_CHUNK);
     static thread_local bool configured = false;
     if (!configured) {   // the largest class needs more than the 48 KB default
-        const int mx = (int)(4 * rn_bp2_warp_bytes(RN_MAX_NCH));
+        const int mx = (int)(4 * rn_bp2_warp_bytes(RN_MAX_NCH) + sizeof(int) * 3 * 1024);
         cudaError_t e = cudaFuncSetAttribute(bp2_kernel<true, kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bp2_kernel<false, kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (e != cudaSuccess) return fail(RN_ERR_CUDA, "bp2 smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     a.nch_max = nch_max;
-    const size_t smem = 4 * rn_bp2_warp_bytes(nch_max);
+    const size_t smem = 4 * rn_bp2_warp_bytes(nch_max) + (kAos ? 0 : rn_bp2_table_bytes(d));
     const unsigned blocks = (unsigned)((a.n + 3) / 4);
     if (first_sweep) bp2_kernel<true, kAos><<<blocks, 128, smem, st>>>(d, a);
     else bp2_kernel<false, kAos><<<blocks, 128, smem, st>>>(d, a);

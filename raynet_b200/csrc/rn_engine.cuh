@@ -43,9 +43,18 @@ __host__ __device__ __forceinline__ int rn_brick(const RnDev &p, int x, int y, i
 
 // ---- PTX: mbarrier + TMA bulk copies (1-D, no tensor map needed) ---------------------------
 __device__ __forceinline__ uint32_t rn_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Canonical use: one thread initialises the CTA's barriers at kernel start, fences, and the
+// whole CTA synchronises before anyone arms or waits on them.
+// Cross-proxy hazard found by the parity tests on B200: a generic-proxy store (st.shared) issued
+// right after try_wait succeeds, to bytes that the bulk copy has written, can lose against the
+// async-proxy write.  The kernels therefore never store into a TMA-written range before they
+// are done reading it (the zero tail of s_hat comes from global memory instead).
 __device__ __forceinline__ void rn_mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rn_mbar_init_fence() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void rn_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -261,15 +270,31 @@ __device__ __forceinline__ void rn_decode_single(const RayHead &h, const uint2 *
 // =======================================================================================
 __device__ __forceinline__ int rn_class_of(int L) { return (L <= 1) ? 0 : ((L + RN_CHUNK - 1) / RN_CHUNK); }
 
-// position t of the tiled enumeration -> ray position k (identity if the segment is not tileable)
+// position t of the tiled enumeration -> ray position k (identity if seg_len <= 0).
+// Pixels are enumerated in 8x8 tiles; when the image is made of whole 64x64 super-tiles the tiles
+// are enumerated super-tile by super-tile, so that the few thousand rays in flight on the GPU
+// at any time form a compact 2-D patch of the image: their epipolar bands in the other views
+// (similarity kernel) and their voxels (BP gathers) then stay L2-resident.  A column-major walk
+// of tiles would make the in-flight set a thin full-height strip whose epipolar fans cover most
+// of every feature map.
 __device__ __forceinline__ int64_t rn_tiled_position(int64_t t, int64_t seg_len, int H) {
     if (seg_len <= 0) return t;
     const int64_t seg = t / seg_len;
     const int tl = (int)(t - seg * seg_len);
-    const int tiles_y = H >> 3;
-    const int tile = tl >> 6, in = tl & 63;
-    const int ty = tile % tiles_y, tx = tile / tiles_y;
-    const int x = tx * 8 + (in >> 3), y = ty * 8 + (in & 7);
+    const int W = (int)(seg_len / H);
+    int x, y;
+    if ((H & 63) == 0 && (W & 63) == 0) {
+        const int st = tl >> 12, rem = tl & 4095;          // 64 tiles of 64 pixels
+        const int sty = st % (H >> 6), stx = st / (H >> 6);
+        const int tile = rem >> 6, in = rem & 63;
+        x = stx * 64 + (tile >> 3) * 8 + (in >> 3);
+        y = sty * 64 + (tile & 7) * 8 + (in & 7);
+    } else {
+        const int tiles_y = H >> 3;
+        const int tile = tl >> 6, in = tl & 63;
+        x = (tile / tiles_y) * 8 + (in >> 3);
+        y = (tile % tiles_y) * 8 + (in & 7);
+    }
     return seg * seg_len + (int64_t)x * H + y;
 }
 
@@ -339,31 +364,57 @@ struct Bp2Args {
 // bytes of dynamic shared memory one warp needs for rays of up to nch chunks:
 //   sS [nch*128] f32  s_hat row, overwritten in place by cp_i * s_i
 //   sM [nch*128] f32  message row, overwritten by w_i, then by the new messages
-//   sLin[nch*128] i32 bricked voxel offsets (lane-consecutive order)
+//   sLin[nch*128] i32 accumulator element offsets (lane-consecutive order)
 //   sCode[nch*8]  u32 step-code words
 //   sPb [nch*32] f32  per-lane prefix base of every chunk;  sTot[pad4(nch)] chunk totals
 //   sX  [128]    f32  transposition scratch
 __host__ __device__ inline size_t rn_bp2_warp_bytes(int nch) {
     return sizeof(float) * ((size_t)nch * (128 * 3 + 8 + 32) + (size_t)((nch + 3) & ~3) + 128);
 }
+// per-CTA header: the three per-axis tables of bricked offsets (resident layout only)
+__host__ __device__ inline size_t rn_bp2_table_bytes(const RnDev &p) {
+    return sizeof(int) * (size_t)((p.gx + p.gy + p.gz + 3) & ~3);
+}
 
 // kAos = the reference's buffers (voxel triplets, raw S clipped + renormalised on the fly as
 // mrf_np.py:306 does, row-major accumulators, rows of any length M): same arithmetic, rows staged
 // with ordinary loads because nothing guarantees the 16-byte alignment TMA needs.
+//
+// Voxels beyond the end of the ray inside its last 128-voxel chunk need no masks in the
+// arithmetic: their s is 0 (so a_i = 0 and nothing reaches the sums), their message input is 0
+// and their step code is "no step", so they alias the last real voxel; only the RED is predicated.
 template <bool kFirst, bool kAos>
 __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
     extern __shared__ __align__(128) unsigned char rn_bp2_smem[];
     __shared__ __align__(8) uint64_t bars[4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nm = a.nch_max;
+
+    // ---- per-axis tables of bricked offsets: lin(x, y, z) = tx[x] + ty[y] + tz[z] -----------
+    int *tabX = reinterpret_cast<int *>(rn_bp2_smem);
+    int *tabY = tabX + p.gx, *tabZ = tabY + p.gy;
+    size_t hdr_bytes = 0;
+    if (!kAos) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int w = 0; w < 4; w++) rn_mbar_init(rn_smem_u32(&bars[w]), 1);
+            rn_mbar_init_fence();
+        }
+        for (int i = threadIdx.x; i < p.gx; i += blockDim.x) tabX[i] = rn_brick_fx(p, i);
+        for (int i = threadIdx.x; i < p.gy; i += blockDim.x) tabY[i] = rn_brick_fy(p, i);
+        for (int i = threadIdx.x; i < p.gz; i += blockDim.x) tabZ[i] = rn_brick_fz(i);
+        hdr_bytes = rn_bp2_table_bytes(p);
+        __syncthreads();
+    }
+
     const int64_t k = (int64_t)blockIdx.x * 4 + wid;
     if (k >= a.n) return;
     const int64_t r = a.order ? (int64_t)__ldg(a.order + a.first + k) : a.first + k;
     const int L = __ldg(a.count + r);
     if (L <= 1) return;   // mrf_np.py:299-301
     const int nch = (L + RN_CHUNK - 1) / RN_CHUNK;
-    const int nm = a.nch_max;
 
-    float *sS = reinterpret_cast<float *>(rn_bp2_smem + (size_t)wid * rn_bp2_warp_bytes(nm));
+    float *sS = reinterpret_cast<float *>(rn_bp2_smem + hdr_bytes + (size_t)wid * rn_bp2_warp_bytes(nm));
     float *sM = sS + nm * 128;
     int *sLin = reinterpret_cast<int *>(sM + nm * 128);
     uint32_t *sCode = reinterpret_cast<uint32_t *>(sLin + nm * 128);
@@ -371,30 +422,31 @@ __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
     float *sTot = sPb + nm * 32;
     float *sX = sTot + ((nm + 3) & ~3);
 
-    // ---- stage the ray's rows with TMA bulk copies -----------------------------------------
+    // ---- stage the ray's rows -----------------------------------------------------------------
     const uint32_t bar = rn_smem_u32(&bars[wid]);
-    const uint32_t row_bytes = (uint32_t)((L + 3) >> 2) << 4;
+    const int L4 = (L + 3) & ~3;
+    const uint32_t row_bytes = (uint32_t)L4 * 4u;
     float *m_row = a.msgs + r * (int64_t)p.row_stride;
     const uint64_t pol_stream = rn_policy_evict_first();
     const uint64_t pol_keep = rn_policy_evict_last();
-    float rawsum = 1.f;
+    float inv_raw = 1.f;
     RayHead head = {0, 0, 0, 1, 1, 1};
     const int32_t *idx_row = nullptr;
     if (kAos) {
         idx_row = a.idx + r * (int64_t)p.M * 3;
         const float *s_row = a.s_hat + r * (int64_t)p.row_stride;
         float part = 0.f;
-        for (int i = lane; i < L; i += 32) {
-            const float v = rn_clampf(s_row[i], 1e-5f, 0.99999f);   // mrf_np.py:4-8
+        for (int i = lane; i < nch * RN_CHUNK; i += 32) {
+            const bool ok = i < L;
+            const float v = ok ? rn_clampf(s_row[i], 1e-5f, 0.99999f) : 0.f;   // mrf_np.py:4-8
             sS[i] = v;
             part += v;
-            if (!kFirst) sM[i] = m_row[i];
+            sM[i] = (!kFirst && ok) ? m_row[i] : 0.f;
         }
-        rawsum = rn_warp_sum(part);
+        inv_raw = 1.0f / rn_warp_sum(part);
         __syncwarp();
     } else {
         if (lane == 0) {
-            rn_mbar_init(bar, 1);
             const uint32_t code_bytes = (uint32_t)nch * 32u;
             rn_mbar_expect_tx(bar, code_bytes + row_bytes * (kFirst ? 1u : 2u));
             rn_bulk_g2s(rn_smem_u32(sCode), a.codes + r * (int64_t)p.code_stride, code_bytes, bar, pol_stream);
@@ -402,29 +454,39 @@ __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
             if (!kFirst) rn_bulk_g2s(rn_smem_u32(sM), m_row, row_bytes, bar, pol_stream);
         }
         head = rn_ray_head(a.hdr + 2 * r);
+        // s = 0 for the slots of the last chunk that the bulk copy does not cover (the front end
+        // stores zeros in s_hat[L .. L4)).  Only s needs it: whatever message or accumulator value
+        // a slot beyond the ray picks up, its a_i = o_i cp_i s_i is 0.  These generic-proxy stores
+        // never touch a byte the async proxy writes.
+        for (int i = L4 + lane; i < nch * RN_CHUNK; i += 32) sS[i] = 0.f;
         __syncwarp();
         rn_mbar_wait(bar, 0);
     }
 
     // ---- forward: gather, occupancy-to-ray, prefix scans ------------------------------------
-    StepCount before = {0, 0, 0};
+    // running table addresses: &tab[coordinate before the current pair], step = +-1 element
+    const int *px = tabX + head.x0, *py = tabY + head.y0, *pz = tabZ + head.z0;
+    const uint32_t le = (2u << lane) - 1u;   // bits <= lane
     float ga[4];
-    // decode chunk c (lane-consecutive), remember the bricked offsets, issue the gathers
+    // decode chunk c (lane-consecutive), remember the accumulator offsets, issue the gathers
     auto issue = [&](int c) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int i = c * RN_CHUNK + 32 * j + lane;
             int lin = 0;
             if (kAos) {
-                if (i < L) lin = rn_lin(p, __ldg(idx_row + 3 * i), __ldg(idx_row + 3 * i + 1), __ldg(idx_row + 3 * i + 2));
+                const int ii = min(i, L - 1);
+                lin = rn_lin(p, __ldg(idx_row + 3 * ii), __ldg(idx_row + 3 * ii + 1), __ldg(idx_row + 3 * ii + 2));
             } else {
                 const uint32_t lo = sCode[c * 8 + 2 * j], hi = sCode[c * 8 + 2 * j + 1];
-                int x, y, z;
-                rn_decode_pair(head, lo, hi, lane, before, x, y, z);
-                lin = rn_brick(p, x, y, z);
+                const uint32_t mx = ~(hi | lo), my = ~hi & lo, mz = hi & ~lo;
+                lin = px[head.sx * __popc(mx & le)] + py[head.sy * __popc(my & le)] + pz[head.sz * __popc(mz & le)];
+                px += head.sx * __popc(mx);
+                py += head.sy * __popc(my);
+                pz += head.sz * __popc(mz);
             }
             sLin[i] = lin;
-            ga[j] = (i < L) ? rn_ld_acc_pol(a.acc_in + lin, pol_keep) : 0.f;
+            ga[j] = rn_ld_acc_pol(a.acc_in + lin, pol_keep);
         }
     };
     issue(0);
@@ -439,17 +501,16 @@ __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
         if (c + 1 < nch) issue(c + 1);   // next chunk's gathers fly while this one is computed
         const int i0 = c * RN_CHUNK + 4 * lane;
         const float4 s4 = *reinterpret_cast<const float4 *>(sS + i0);
-        float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!kFirst) m4 = *reinterpret_cast<const float4 *>(sM + i0);
+        float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);   // first sweep: messages are 0 (mrf_np.py:275)
+        if (!kFirst || kAos) m4 = *reinterpret_cast<const float4 *>(sM + i0);
         const float accv[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
         const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
         float sv[4] = {s4.x, s4.y, s4.z, s4.w};
         float w[4], o[4], q[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const bool ok = i0 + j < L;
-            w[j] = ok ? rn_occ_w(accv[j], mv[j]) : 0.f;   // invalid: o = 0, 1 - o = 1, s = 0 -> neutral
-            sv[j] = ok ? (kAos ? sv[j] / rawsum : sv[j]) : 0.f;
+            w[j] = rn_occ_w(accv[j], mv[j]);
+            if (kAos) sv[j] *= inv_raw;
             rn_occ_from_w(w[j], o[j], q[j]);
         }
         // exclusive products cp_i = prod_{k<i} (1 - o_k)
@@ -505,17 +566,24 @@ __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
             const float pos = pre + cps[j];
             const float neg = fmaf(suf[j], rn_rcp(q[j]), pre);
             // log p - log(1 - p) with p = pos / (pos + neg)
-            msg[j] = (i0 + j < L) ? 0.6931471805599453f * rn_lg2(pos * rn_rcp(neg)) : 0.f;
+            msg[j] = 0.6931471805599453f * rn_lg2(pos * rn_rcp(neg));
             pre += av[j];
         }
         carry_suf += sTot[c];
-        __syncwarp();
         *reinterpret_cast<float4 *>(sM + i0) = make_float4(msg[0], msg[1], msg[2], msg[3]);
         __syncwarp();
+        if (c < nch - 1) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int i = c * RN_CHUNK + 32 * j + lane;
-            if (i < L) rn_red_add_pol(a.acc_out + sLin[i], sM[i], pol_keep);
+            for (int j = 0; j < 4; j++) {
+                const int i = c * RN_CHUNK + 32 * j + lane;
+                rn_red_add_pol(a.acc_out + sLin[i], sM[i], pol_keep);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = c * RN_CHUNK + 32 * j + lane;
+                if (i < L) rn_red_add_pol(a.acc_out + sLin[i], sM[i], pol_keep);
+            }
         }
     }
     if (kAos) {

@@ -390,9 +390,12 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
         if (kAos) {
             for (int i = lane; i < L; i += 32) out_row[i] = sVal[i] * inv_c;
         } else {   // resident rows are 16-byte aligned and padded to whole chunks
-            for (int i = 4 * lane; i < L; i += 128) {
+            for (int i = 4 * lane; i < L; i += 128) {   // the last quad is zero-filled beyond L (bp2_kernel relies on it)
                 float4 v = *reinterpret_cast<const float4 *>(sVal + i);
-                v.x *= inv_c; v.y *= inv_c; v.z *= inv_c; v.w *= inv_c;
+                v.x *= inv_c;
+                v.y = (i + 1 < L) ? v.y * inv_c : 0.f;
+                v.z = (i + 2 < L) ? v.z * inv_c : 0.f;
+                v.w = (i + 3 < L) ? v.w * inv_c : 0.f;
                 rn_st_stream4(out_row + i, v);
             }
         }

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "rn_kernels.cuh"
 
@@ -110,6 +111,7 @@ int launch_simmap(const RnDev &d, SimMapArgs a, bool mapping, cudaStream_t st) {
     if (!mapping) a.count = nullptr;
     a.val_stride = mapping ? (int)row_stride_of(d.M) : 0;
     a.tile_len = tile_len_for(d, a.n_rays);
+    { const char *m = getenv("RN_TILE_MODE"); a.tile_mode = m ? atoi(m) : 2; }
     const size_t smem = rn_simmap_smem_bytes(d.D, d.V, a.val_stride, warps);
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {

@@ -277,18 +277,23 @@ __device__ __forceinline__ int rn_class_of(int L) { return (L <= 1) ? 0 : ((L + 
 // (similarity kernel) and their voxels (BP gathers) then stay L2-resident.  A column-major walk
 // of tiles would make the in-flight set a thin full-height strip whose epipolar fans cover most
 // of every feature map.
-__device__ __forceinline__ int64_t rn_tiled_position(int64_t t, int64_t seg_len, int H) {
-    if (seg_len <= 0) return t;
+__device__ __forceinline__ int64_t rn_tiled_position(int64_t t, int64_t seg_len, int H, int mode = 2) {
+    if (seg_len <= 0 || mode == 0) return t;
     const int64_t seg = t / seg_len;
     const int tl = (int)(t - seg * seg_len);
     const int W = (int)(seg_len / H);
     int x, y;
-    if ((H & 63) == 0 && (W & 63) == 0) {
+    if (mode == 2 && (H & 63) == 0 && (W & 63) == 0) {
         const int st = tl >> 12, rem = tl & 4095;          // 64 tiles of 64 pixels
         const int sty = st % (H >> 6), stx = st / (H >> 6);
         const int tile = rem >> 6, in = rem & 63;
         x = stx * 64 + (tile >> 3) * 8 + (in >> 3);
         y = sty * 64 + (tile & 7) * 8 + (in & 7);
+    } else if (mode == 3) {                                // tiles row-major: 8-pixel-tall strips
+        const int tiles_x = W >> 3;
+        const int tile = tl >> 6, in = tl & 63;
+        x = (tile % tiles_x) * 8 + (in >> 3);
+        y = (tile / tiles_x) * 8 + (in & 7);
     } else {
         const int tiles_y = H >> 3;
         const int tile = tl >> 6, in = tl & 63;

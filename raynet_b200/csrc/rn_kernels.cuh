@@ -136,6 +136,7 @@ struct SimMapArgs {
     int64_t n_rays;
     int64_t tile_len;          // > 0: warps walk the rays in 8x8-pixel tiles (rn_tiled_position)
     int val_stride;            // floats of the per-warp voxel buffer (0 without mapping stage)
+    int tile_mode;
 };
 
 // dynamic shared memory: per CTA [V*12 P][12 P_inv][4 C][V view slots], per warp
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
 
     const int64_t t = (int64_t)blockIdx.x * warps + wid;
     if (t >= a.n_rays) return;
-    const int64_t r = rn_tiled_position(t, a.tile_len, p.H);
+    const int64_t r = rn_tiled_position(t, a.tile_len, p.H, a.tile_mode);
 
     // ---- a1: ray start / end -------------------------------------------------------
     float rs[3], re[3];

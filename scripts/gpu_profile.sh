@@ -9,7 +9,7 @@ B="python bench.py --config $CFG --steps 1 --warmup 1 --no-cpu --no-e2e"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${CFG}_${TAG}.csv \
     $B > gpurun_out/bench_under_ncu_${CFG}_${TAG}.log 2>&1
 for K in ${KERNELS:-bp_kernel simmap_kernel}; do
-  ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 1 -f \
+  ncu --set full --clock-control none --import-source on -k regex:$K -s ${SKIP:-2} -c 1 -f \
       -o gpurun_out/prof_${K}_${CFG}_${TAG} $B > gpurun_out/prof_${K}_${CFG}_${TAG}.log 2>&1
 done
 ls -la gpurun_out

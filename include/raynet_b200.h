@@ -169,6 +169,8 @@ int rn_mvcnn_voxel_depth(const RnParams *p, const int32_t *ray_idxs, const float
  *             of 32-bit bit planes per 32 voxels; code = the axis stepped along to ENTER the
  *             voxel, 3 = none (0.25 B / voxel).  rn_code_stride(M) = bytes per ray.
  *   count     int32  [n]
+ *   lin       int32  [n][R]  bricked accumulator offset of every traversed voxel (4 B / voxel), so
+ *             that a sweep gathers / scatter-adds without re-deriving coordinates
  *   s_hat     float32 [n][R]  clip_and_renorm(S_voxel_space[r, :count])  (mrf_np.py:4-8)
  *   msgs      float32 [n][R]
  * The two occupancy accumulators of the resident pipeline are BRICKED (4x4x2-voxel 128-byte
@@ -186,7 +188,7 @@ int rn_grid_to_bricks(const RnParams *p, const float *grid, float *bricks, float
 int rn_bricks_to_grid(const RnParams *p, const float *bricks, float *grid, int apply_sigmoid, void *stream);
 
 /* Front end once per reference image: fills starts/ends (may be NULL), ray_hdr, codes,
- * count, s_hat.  axis_centres: float32 [Gx+Gy+Gz] voxel-centre coordinates per axis
+ * count, s_hat, lin.  axis_centres: float32 [Gx+Gy+Gz] voxel-centre coordinates per axis
  * (rn_axis_centres extracts them from the reference's voxel_grid table).
  * view_ids (may be NULL): int32 [V], the slot inside `features` of each of the V views of
  * this reference image, so that one resident feature volume [n_feature_slots][H+p+1][W+p+1][F]
@@ -196,7 +198,7 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
                        const int32_t *view_ids, int32_t n_feature_slots, const float *P,
                        const float *P_inv, const float *centre, const float *axis_centres, float *starts,
                        float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *s_hat,
-                       int64_t n_rays, void *stream);
+                       int32_t *lin, int64_t n_rays, void *stream);
 
 /* Group the rays by length class (class c = ceil(count / 128) for count >= 2, class 0 = the rays
  * BP skips) so that each class runs with the shared memory its rays need.  order: int32 [n]
@@ -213,7 +215,7 @@ int rn_engine_bin_rays(const RnParams *p, const int32_t *count, int64_t n_rays, 
  * order / class_offsets (HOST int64 [rn_num_classes() + 1], may both be NULL): the binning of
  * rn_engine_bin_rays.  first_sweep != 0: messages are taken as all-zero and not read
  * (mrf_np.py:275).  max_count: upper bound on count[] (used when there is no binning). */
-int rn_engine_bp_iteration(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes,
+int rn_engine_bp_iteration(const RnParams *p, const int32_t *lin,
                            const int32_t *count, const float *s_hat, float *msgs, const float *acc_in,
                            float *acc_out, const int32_t *order, const int64_t *class_offsets,
                            int32_t first_sweep, int32_t max_count, int64_t n_rays, void *stream);
@@ -222,7 +224,7 @@ int rn_engine_bp_iteration(const RnParams *p, const uint32_t *ray_hdr, const uin
  * depth_map[r] = |centre(voxel argmax_i o_i cp_i s_i) - C_image(r)|.  centres: float32 [n_seg][4];
  * seg_starts: device int64 [n_seg + 1], first ray of every image (ignored when n_seg == 1).
  * S_new (may be NULL): float32 [n][R], the normalised depth distribution (parity tests). */
-int rn_engine_depth(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count,
+int rn_engine_depth(const RnParams *p, const int32_t *lin, const int32_t *count,
                     const float *s_hat, const float *msgs, const float *acc, const float *axis_centres,
                     const float *centres, const int64_t *seg_starts, int32_t n_seg, float *depth_map,
                     float *S_new, int64_t n_rays, void *stream);

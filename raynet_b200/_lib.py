@@ -67,10 +67,10 @@ SIGNATURES = {
     "rn_raynet_de": [_PP] + [_PTR] * 12 + [_I64, _PTR],
     "rn_mvcnn_voxel": [_PP] + [_PTR] * 9 + [_I64, _PTR],
     "rn_mvcnn_voxel_depth": [_PP] + [_PTR] * 10 + [_I64, _PTR],
-    "rn_engine_frontend": [_PP, _PTR, _PTR, _PTR, _I32] + [_PTR] * 10 + [_I64, _PTR],
+    "rn_engine_frontend": [_PP, _PTR, _PTR, _PTR, _I32] + [_PTR] * 11 + [_I64, _PTR],
     "rn_engine_bin_rays": [_PP, _PTR, _I64, _I64, _PTR, _PTR, _PTR],
-    "rn_engine_bp_iteration": [_PP] + [_PTR] * 9 + [_I32, _I32, _I64, _PTR],
-    "rn_engine_depth": [_PP] + [_PTR] * 9 + [_I32, _PTR, _PTR, _I64, _PTR],
+    "rn_engine_bp_iteration": [_PP] + [_PTR] * 8 + [_I32, _I32, _I64, _PTR],
+    "rn_engine_depth": [_PP] + [_PTR] * 8 + [_I32, _PTR, _PTR, _I64, _PTR],
     "rn_grid_to_bricks": [_PP, _PTR, _PTR, ctypes.c_float, _PTR],
     "rn_bricks_to_grid": [_PP, _PTR, _PTR, _I32, _PTR],
     "rn_engine_expand_indices": [_PP, _PTR, _PTR, _PTR, _PTR, _I64, _PTR],

@@ -132,14 +132,14 @@ int launch_bp2(const RnDev &d, Bp2Args a, bool first_sweep, int nch_max, cudaStr
         return fail(RN_ERR_UNSUPPORTED, "rays longer than %d voxels are not supported", RN_MAX_NCH * RN_CHUNK);
     static thread_local bool configured = false;
     if (!configured) {   // the largest class needs more than the 48 KB default
-        const int mx = (int)(4 * rn_bp2_warp_bytes(RN_MAX_NCH) + sizeof(int) * 3 * 1024);
+        const int mx = (int)(4 * rn_bp2_warp_bytes(RN_MAX_NCH));
         cudaError_t e = cudaFuncSetAttribute(bp2_kernel<true, kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bp2_kernel<false, kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (e != cudaSuccess) return fail(RN_ERR_CUDA, "bp2 smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     a.nch_max = nch_max;
-    const size_t smem = 4 * rn_bp2_warp_bytes(nch_max) + (kAos ? 0 : rn_bp2_table_bytes(d));
+    const size_t smem = 4 * rn_bp2_warp_bytes(nch_max);
     const unsigned blocks = (unsigned)((a.n + 3) / 4);
     if (first_sweep) bp2_kernel<true, kAos><<<blocks, 128, smem, st>>>(d, a);
     else bp2_kernel<false, kAos><<<blocks, 128, smem, st>>>(d, a);
@@ -489,7 +489,7 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
                        const int32_t *view_ids, int32_t n_feature_slots, const float *P,
                        const float *P_inv, const float *centre, const float *axis_centres, float *starts,
                        float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *s_hat,
-                       int64_t n_rays, void *stream) {
+                       int32_t *lin, int64_t n_rays, void *stream) {
     RnDev d;
     int rc = make_dev(p, d, true, true, true);
     if (rc) return rc;
@@ -512,7 +512,8 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
     SimMapArgs a = {};
     a.starts_in = starts; a.ends_in = ends;
     a.ray_idxs = ray_idxs; a.features = features; a.view_ids = view_ids; a.P = P; a.P_inv = P_inv; a.centre = centre;
-    a.axes = axis_centres; a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.n_rays = n_rays;
+    a.axes = axis_centres; a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.lin = lin;
+    a.n_rays = n_rays;
     return launch_simmap<false>(d, a, true, S(stream));
 }
 
@@ -538,7 +539,7 @@ int rn_engine_bin_rays(const RnParams *p, const int32_t *count, int64_t n_rays, 
     return check_launch("bin_scatter_kernel");
 }
 
-int rn_engine_bp_iteration(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes,
+int rn_engine_bp_iteration(const RnParams *p, const int32_t *lin,
                            const int32_t *count, const float *s_hat, float *msgs, const float *acc_in,
                            float *acc_out, const int32_t *order, const int64_t *class_offsets,
                            int32_t first_sweep, int32_t max_count, int64_t n_rays, void *stream) {
@@ -547,7 +548,7 @@ int rn_engine_bp_iteration(const RnParams *p, const uint32_t *ray_hdr, const uin
     if (rc) return rc;
     if (max_count <= 0 || max_count > d.M) max_count = d.M;
     Bp2Args a = {};
-    a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.msgs = msgs; a.acc_in = acc_in;
+    a.lin = lin; a.count = count; a.s_hat = s_hat; a.msgs = msgs; a.acc_in = acc_in;
     a.acc_out = acc_out;
     if (!order || !class_offsets) {   // no binning: one launch sized for the longest ray
         a.first = 0; a.n = n_rays;
@@ -564,7 +565,7 @@ int rn_engine_bp_iteration(const RnParams *p, const uint32_t *ray_hdr, const uin
     return RN_OK;
 }
 
-int rn_engine_depth(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count,
+int rn_engine_depth(const RnParams *p, const int32_t *lin, const int32_t *count,
                     const float *s_hat, const float *msgs, const float *acc, const float *axis_centres,
                     const float *centres, const int64_t *seg_starts, int32_t n_seg, float *depth_map,
                     float *S_new, int64_t n_rays, void *stream) {
@@ -573,7 +574,7 @@ int rn_engine_depth(const RnParams *p, const uint32_t *ray_hdr, const uint8_t *c
     if (rc) return rc;
     if (n_seg < 1) return fail(RN_ERR_SHAPE, "n_seg must be at least 1");
     Depth2Args a = {};
-    a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.msgs = msgs; a.acc = acc;
+    a.lin = lin; a.count = count; a.s_hat = s_hat; a.msgs = msgs; a.acc = acc;
     a.axes = axis_centres; a.centres = centres; a.seg_starts = (n_seg > 1) ? seg_starts : nullptr; a.n_seg = n_seg;
     a.depth_map = depth_map; a.S_new = S_new; a.n_rays = n_rays;
     return launch_depth2<false>(d, a, S(stream));

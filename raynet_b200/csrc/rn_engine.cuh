@@ -41,6 +41,15 @@ __host__ __device__ __forceinline__ int rn_brick(const RnDev &p, int x, int y, i
     return rn_brick_fx(p, x) + rn_brick_fy(p, y) + rn_brick_fz(z);
 }
 
+__host__ __device__ __forceinline__ void rn_unbrick(const RnDev &p, int off, int &x, int &y, int &z) {
+    const int line = off >> 5, in = off & 31;
+    const int lz = line % p.blz, t = line / p.blz;
+    const int by = t % p.bby, bx = t / p.bby;
+    x = bx * 4 + ((in >> 4) & 1) * 2 + ((in >> 2) & 1);
+    y = by * 4 + ((in >> 3) & 1) * 2 + ((in >> 1) & 1);
+    z = lz * 2 + (in & 1);
+}
+
 // ---- PTX: mbarrier + TMA bulk copies (1-D, no tensor map needed) ---------------------------
 __device__ __forceinline__ uint32_t rn_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // Canonical use: one thread initialises the CTA's barriers at kernel start, fences, and the
@@ -352,8 +361,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const int32_t *count, 
 // a5 + a6: one BP sweep, warp per ray, state staged in shared memory
 // =======================================================================================
 struct Bp2Args {
-    const uint32_t *hdr;    // resident layout
-    const uint8_t *codes;   // resident layout
+    const int32_t *lin;     // resident layout: int32 [n][row_stride] bricked accumulator offset of every voxel
     const int32_t *idx;     // reference layout (kAos): int32 [n][M][3]
     const int32_t *count;
     const float *s_hat;     // resident: clip_and_renorm'ed rows; kAos: raw S_voxel_space rows
@@ -369,18 +377,13 @@ struct Bp2Args {
 // bytes of dynamic shared memory one warp needs for rays of up to nch chunks:
 //   sS [nch*128] f32  s_hat row, overwritten in place by cp_i * s_i
 //   sM [nch*128] f32  message row, overwritten by w_i, then by the new messages
-//   sLin[nch*128] i32 accumulator element offsets (lane-consecutive order)
-//   sCode[nch*8]  u32 step-code words
+//   sLin[nch*128] i32 accumulator element offsets of the voxels
+//   (8 words per chunk unused)
 //   sPb [nch*32] f32  per-lane prefix base of every chunk;  sTot[pad4(nch)] chunk totals
 //   sX  [128]    f32  transposition scratch
 __host__ __device__ inline size_t rn_bp2_warp_bytes(int nch) {
     return sizeof(float) * ((size_t)nch * (128 * 3 + 8 + 32) + (size_t)((nch + 3) & ~3) + 128);
 }
-// per-CTA header: the three per-axis tables of bricked offsets (resident layout only)
-__host__ __device__ inline size_t rn_bp2_table_bytes(const RnDev &p) {
-    return sizeof(int) * (size_t)((p.gx + p.gy + p.gz + 3) & ~3);
-}
-
 // kAos = the reference's buffers (voxel triplets, raw S clipped + renormalised on the fly as
 // mrf_np.py:306 does, row-major accumulators, rows of any length M): same arithmetic, rows staged
 // with ordinary loads because nothing guarantees the 16-byte alignment TMA needs.
@@ -395,20 +398,12 @@ __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nm = a.nch_max;
 
-    // ---- per-axis tables of bricked offsets: lin(x, y, z) = tx[x] + ty[y] + tz[z] -----------
-    int *tabX = reinterpret_cast<int *>(rn_bp2_smem);
-    int *tabY = tabX + p.gx, *tabZ = tabY + p.gy;
-    size_t hdr_bytes = 0;
     if (!kAos) {
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int w = 0; w < 4; w++) rn_mbar_init(rn_smem_u32(&bars[w]), 1);
             rn_mbar_init_fence();
         }
-        for (int i = threadIdx.x; i < p.gx; i += blockDim.x) tabX[i] = rn_brick_fx(p, i);
-        for (int i = threadIdx.x; i < p.gy; i += blockDim.x) tabY[i] = rn_brick_fy(p, i);
-        for (int i = threadIdx.x; i < p.gz; i += blockDim.x) tabZ[i] = rn_brick_fz(i);
-        hdr_bytes = rn_bp2_table_bytes(p);
         __syncthreads();
     }
 
@@ -419,11 +414,10 @@ __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
     if (L <= 1) return;   // mrf_np.py:299-301
     const int nch = (L + RN_CHUNK - 1) / RN_CHUNK;
 
-    float *sS = reinterpret_cast<float *>(rn_bp2_smem + hdr_bytes + (size_t)wid * rn_bp2_warp_bytes(nm));
+    float *sS = reinterpret_cast<float *>(rn_bp2_smem + (size_t)wid * rn_bp2_warp_bytes(nm));
     float *sM = sS + nm * 128;
     int *sLin = reinterpret_cast<int *>(sM + nm * 128);
-    uint32_t *sCode = reinterpret_cast<uint32_t *>(sLin + nm * 128);
-    float *sPb = reinterpret_cast<float *>(sCode + nm * 8);
+    float *sPb = reinterpret_cast<float *>(sLin + nm * 128 + nm * 8);
     float *sTot = sPb + nm * 32;
     float *sX = sTot + ((nm + 3) & ~3);
 
@@ -435,7 +429,6 @@ __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
     const uint64_t pol_stream = rn_policy_evict_first();
     const uint64_t pol_keep = rn_policy_evict_last();
     float inv_raw = 1.f;
-    RayHead head = {0, 0, 0, 1, 1, 1};
     const int32_t *idx_row = nullptr;
     if (kAos) {
         idx_row = a.idx + r * (int64_t)p.M * 3;
@@ -452,13 +445,11 @@ __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
         __syncwarp();
     } else {
         if (lane == 0) {
-            const uint32_t code_bytes = (uint32_t)nch * 32u;
-            rn_mbar_expect_tx(bar, code_bytes + row_bytes * (kFirst ? 1u : 2u));
-            rn_bulk_g2s(rn_smem_u32(sCode), a.codes + r * (int64_t)p.code_stride, code_bytes, bar, pol_stream);
+            rn_mbar_expect_tx(bar, row_bytes * (kFirst ? 2u : 3u));
+            rn_bulk_g2s(rn_smem_u32(sLin), a.lin + r * (int64_t)p.row_stride, row_bytes, bar, pol_stream);
             rn_bulk_g2s(rn_smem_u32(sS), a.s_hat + r * (int64_t)p.row_stride, row_bytes, bar, pol_stream);
             if (!kFirst) rn_bulk_g2s(rn_smem_u32(sM), m_row, row_bytes, bar, pol_stream);
         }
-        head = rn_ray_head(a.hdr + 2 * r);
         // s = 0 for the slots of the last chunk that the bulk copy does not cover (the front end
         // stores zeros in s_hat[L .. L4)).  Only s needs it: whatever message or accumulator value
         // a slot beyond the ray picks up, its a_i = o_i cp_i s_i is 0.  These generic-proxy stores
@@ -469,29 +460,23 @@ __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
     }
 
     // ---- forward: gather, occupancy-to-ray, prefix scans ------------------------------------
-    // running table addresses: &tab[coordinate before the current pair], step = +-1 element
-    const int *px = tabX + head.x0, *py = tabY + head.y0, *pz = tabZ + head.z0;
-    const uint32_t le = (2u << lane) - 1u;   // bits <= lane
     float ga[4];
-    // decode chunk c (lane-consecutive), remember the accumulator offsets, issue the gathers
+    // issue the accumulator gathers of chunk c: lane-consecutive voxels share sectors.  Slots
+    // beyond the ray (last chunk only) gather nothing; their value is irrelevant (s = 0).
     auto issue = [&](int c) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int i = c * RN_CHUNK + 32 * j + lane;
-            int lin = 0;
             if (kAos) {
                 const int ii = min(i, L - 1);
-                lin = rn_lin(p, __ldg(idx_row + 3 * ii), __ldg(idx_row + 3 * ii + 1), __ldg(idx_row + 3 * ii + 2));
+                const int lin = rn_lin(p, __ldg(idx_row + 3 * ii), __ldg(idx_row + 3 * ii + 1), __ldg(idx_row + 3 * ii + 2));
+                sLin[i] = lin;
+                ga[j] = rn_ld_acc_pol(a.acc_in + lin, pol_keep);
+            } else if (c < nch - 1 || i < L) {
+                ga[j] = rn_ld_acc_pol(a.acc_in + sLin[i], pol_keep);
             } else {
-                const uint32_t lo = sCode[c * 8 + 2 * j], hi = sCode[c * 8 + 2 * j + 1];
-                const uint32_t mx = ~(hi | lo), my = ~hi & lo, mz = hi & ~lo;
-                lin = px[head.sx * __popc(mx & le)] + py[head.sy * __popc(my & le)] + pz[head.sz * __popc(mz & le)];
-                px += head.sx * __popc(mx);
-                py += head.sy * __popc(my);
-                pz += head.sz * __popc(mz);
+                ga[j] = 0.f;
             }
-            sLin[i] = lin;
-            ga[j] = rn_ld_acc_pol(a.acc_in + lin, pol_keep);
         }
     };
     issue(0);
@@ -610,8 +595,7 @@ __global__ void __launch_bounds__(128) bp2_kernel(RnDev p, Bp2Args a) {
 // a8 + a9: depth re-estimation + arg-max -> depth, warp per ray, all images in one launch
 // =======================================================================================
 struct Depth2Args {
-    const uint32_t *hdr;
-    const uint8_t *codes;
+    const int32_t *lin;        // resident: int32 [n][row_stride] bricked offsets
     const int32_t *idx;        // kAos
     const int32_t *count;
     const float *s_hat;
@@ -641,15 +625,10 @@ __global__ void __launch_bounds__(128) depth2_kernel(RnDev p, Depth2Args a) {
         if (__ldg(a.seg_starts + mid) <= r) lo_s = mid; else hi_s = mid;
     }
     const float *C = a.centres ? a.centres + 4 * lo_s : nullptr;
-    RayHead head = {0, 0, 0, 1, 1, 1};
-    const uint2 *words = nullptr;
+    const int32_t *lin_row = nullptr;
     const int32_t *idx_row = nullptr;
-    if (kAos) {
-        idx_row = a.idx + r * (int64_t)p.M * 3;
-    } else {
-        head = rn_ray_head(a.hdr + 2 * r);
-        words = reinterpret_cast<const uint2 *>(a.codes + r * (int64_t)p.code_stride);
-    }
+    if (kAos) idx_row = a.idx + r * (int64_t)p.M * 3;
+    else lin_row = a.lin + r * (int64_t)p.row_stride;
     const float *s_row = a.s_hat + r * (int64_t)p.row_stride;
     const float *m_row = a.msgs + r * (int64_t)p.row_stride;
     float rawsum = 1.f;
@@ -665,7 +644,6 @@ __global__ void __launch_bounds__(128) depth2_kernel(RnDev p, Depth2Args a) {
     const uint64_t pol_keep = rn_policy_evict_last();
     if (L > 1) {   // mrf_np.py:376-377: rays with count <= 1 keep an all-zero row
         const int nch = (L + RN_CHUNK - 1) / RN_CHUNK;
-        StepCount before = {0, 0, 0};
         float carry_cp = 1.f;
         for (int c = 0; c < nch; c++) {
             float ga[4];
@@ -675,11 +653,8 @@ __global__ void __launch_bounds__(128) depth2_kernel(RnDev p, Depth2Args a) {
                 int lin = 0;
                 if (kAos) {
                     if (i < L) lin = rn_lin(p, __ldg(idx_row + 3 * i), __ldg(idx_row + 3 * i + 1), __ldg(idx_row + 3 * i + 2));
-                } else {
-                    const uint2 cw = __ldg(words + c * 4 + j);
-                    int x, y, z;
-                    rn_decode_pair(head, cw.x, cw.y, lane, before, x, y, z);
-                    lin = rn_brick(p, x, y, z);
+                } else if (i < L) {
+                    lin = __ldg(lin_row + i);
                 }
                 ga[j] = (i < L) ? rn_ld_acc_pol(a.acc + lin, pol_keep) : 0.f;
             }
@@ -764,7 +739,7 @@ __global__ void __launch_bounds__(128) depth2_kernel(RnDev p, Depth2Args a) {
         if (kAos) {
             if (L >= 1) { x = idx_row[3 * sel]; y = idx_row[3 * sel + 1]; z = idx_row[3 * sel + 2]; }
         } else if (L >= 1) {
-            rn_decode_single(head, words, sel, x, y, z);
+            rn_unbrick(p, __ldg(lin_row + sel), x, y, z);
         }
         const float cc[3] = {__ldg(a.axes + x), __ldg(a.axes + p.gx + y), __ldg(a.axes + p.gx + p.gy + z)};
         float sum = 0.f;
@@ -782,12 +757,8 @@ __global__ void grid_to_bricks_kernel(RnDev p, const float *grid, float *bricks,
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_bricked; b += stride) {
         // invert the brick offset
-        const int line = (int)(b >> 5), in = (int)(b & 31);
-        const int lz = line % p.blz, t = line / p.blz;
-        const int by = t % p.bby, bx = t / p.bby;
-        const int x = bx * 4 + ((in >> 4) & 1) * 2 + ((in >> 2) & 1);
-        const int y = by * 4 + ((in >> 3) & 1) * 2 + ((in >> 1) & 1);
-        const int z = lz * 2 + (in & 1);
+        int x, y, z;
+        rn_unbrick(p, (int)b, x, y, z);
         bricks[b] = (x < p.gx && y < p.gy && z < p.gz) ? grid[rn_lin(p, x, y, z)] : pad;
     }
 }

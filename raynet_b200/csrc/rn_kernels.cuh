@@ -132,6 +132,7 @@ struct SimMapArgs {
     const int32_t *count;
     float *S_vox;              // [n][row_stride] optional out: normalised S_voxel_space
     float *s_hat;              // [n][row_stride] optional out: clip_and_renorm(S_voxel_space)
+    int32_t *lin;              // [n][row_stride] optional out (!kAos): bricked accumulator offset of every voxel
     float *depth_vox;          // [n] optional out: |centre(argmax voxel of S_vox) - C|
     int64_t n_rays;
     int64_t tile_len;          // > 0: warps walk the rays in 8x8-pixel tiles (rn_tiled_position)
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(128) simmap_kernel(RnDev p, SimMapArgs a) {
                 rn_decode_pair(head, cw.x, cw.y, lane, before, vx, vy, vz);
             }
             if (i < L) {
+                if (!kAos && a.lin) a.lin[r * (int64_t)p.row_stride + i] = rn_brick(p, vx, vy, vz);
                 float cc[3] = {__ldg(a.axes + vx), __ldg(a.axes + p.gx + vy), __ldg(a.axes + p.gx + p.gy + vz)};
                 float sum = 0.f;
 #pragma unroll

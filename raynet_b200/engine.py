@@ -66,6 +66,7 @@ class RayPotentialEngine(object):
         self.hdr = torch.zeros((n, 2), dtype=torch.int32, **kw)
         self.codes = torch.zeros((n, self.code_stride), dtype=torch.uint8, **kw)
         self.count = torch.zeros((n,), dtype=torch.int32, **kw)
+        self.lin = torch.empty((n, self.R), dtype=torch.int32, **kw)
         self.s_hat = torch.empty((n, self.R), dtype=torch.float32, **kw)
         self.msgs = torch.empty((n, self.R), dtype=torch.float32, **kw)
         self.order = torch.zeros((n,), dtype=torch.int32, **kw)
@@ -133,7 +134,7 @@ class RayPotentialEngine(object):
         _lib.call("rn_engine_frontend", self.params, _ptr(ray_idxs), _ptr(features),
                   _ptr(view_ids) if view_ids is not None else None, slots, _ptr(P), _ptr(P_inv), _ptr(centre),
                   _ptr(self.axes), _ptr(starts), _ptr(ends), _ptr(self.hdr[sl]), _ptr(self.codes[sl]),
-                  _ptr(self.count[sl]), _ptr(self.s_hat[sl]), n, current_stream_ptr())
+                  _ptr(self.count[sl]), _ptr(self.s_hat[sl]), _ptr(self.lin[sl]), n, current_stream_ptr())
         self.launches += 2
         self.segments.append((start, n, centre))
         self.n_rays = start + n
@@ -171,7 +172,7 @@ class RayPotentialEngine(object):
         if self.sweep_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        _lib.call("rn_engine_bp_iteration", self.params, _ptr(self.hdr), _ptr(self.codes), _ptr(self.count),
+        _lib.call("rn_engine_bp_iteration", self.params, _ptr(self.lin), _ptr(self.count),
                   _ptr(self.s_hat), _ptr(self.msgs), _ptr(self.acc_prev), _ptr(self.acc_new), _ptr(self.order),
                   self._class_offsets, 1 if self.iterations_done == 0 else 0, int(self.max_count), self.n_rays, st)
         if self.sweep_events is not None:
@@ -225,7 +226,7 @@ class RayPotentialEngine(object):
             depth_out = torch.empty((self.n_rays,), dtype=torch.float32, device=self.dev)
         if self.iterations_done == 0:
             self.msgs[:self.n_rays].zero_()
-        _lib.call("rn_engine_depth", self.params, _ptr(self.hdr), _ptr(self.codes), _ptr(self.count), _ptr(self.s_hat),
+        _lib.call("rn_engine_depth", self.params, _ptr(self.lin), _ptr(self.count), _ptr(self.s_hat),
                   _ptr(self.msgs), _ptr(self.acc_prev), _ptr(self.axes), _ptr(self._centres), _ptr(self._seg_starts),
                   len(self.segments), _ptr(depth_out), _ptr(S_new), self.n_rays, current_stream_ptr())
         self.launches += 1

@@ -6,6 +6,8 @@
 #include <cstdlib>
 
 #include "rn_kernels.cuh"
+#include "rn_bp3.cuh"
+#include "rn_bp4.cuh"
 
 namespace {
 
@@ -144,6 +146,69 @@ int launch_bp2(const RnDev &d, Bp2Args a, bool first_sweep, int nch_max, cudaStr
     if (first_sweep) bp2_kernel<true, kAos><<<blocks, 128, smem, st>>>(d, a);
     else bp2_kernel<false, kAos><<<blocks, 128, smem, st>>>(d, a);
     return check_launch("bp2_kernel");
+}
+
+// Register-resident sweep for one length class (rays of exactly nch chunks), resident layout only.
+template <int NCH>
+int launch_bp3_n(const RnDev &d, const Bp2Args &a, bool first_sweep, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((a.n + RN_BP3_RAYS_PER_CTA - 1) / RN_BP3_RAYS_PER_CTA);
+    if (a.debug & 8) {
+        bp_memonly_kernel<NCH><<<(unsigned)((a.n + 3) / 4), 128, 0, st>>>(d, a);
+        return check_launch("bp_memonly_kernel");
+    }
+    if (first_sweep) bp3_kernel<NCH, true><<<blocks, 128, 0, st>>>(d, a);
+    else bp3_kernel<NCH, false><<<blocks, 128, 0, st>>>(d, a);
+    return check_launch("bp3_kernel");
+}
+
+// Prefetching register-resident sweep (rn_bp4.cuh); every ray of the launch has exactly NCH chunks.
+template <int NCH, bool kFirst>
+int launch_bp4_nf(const RnDev &d, const Bp2Args &a, cudaStream_t st) {
+    const size_t smem = (size_t)4 * rn_bp4_warp_words(NCH, kFirst) * sizeof(float);
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(bp4_kernel<NCH, kFirst>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "bp4 smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int per_cta = 4 * RN_BP4_RAYS_PER_WARP;
+    const unsigned blocks = (unsigned)((a.n + per_cta - 1) / per_cta);
+    bp4_kernel<NCH, kFirst><<<blocks, 128, smem, st>>>(d, a);
+    return check_launch("bp4_kernel");
+}
+template <int NCH>
+int launch_bp4_n(const RnDev &d, const Bp2Args &a, bool first_sweep, cudaStream_t st) {
+    return first_sweep ? launch_bp4_nf<NCH, true>(d, a, st) : launch_bp4_nf<NCH, false>(d, a, st);
+}
+
+#define RN_BP3_MAX_NCH 6
+// exact_class: every ray of the launch has exactly nch chunks (binned launches)
+int launch_bp_class(const RnDev &d, Bp2Args a, bool first_sweep, int nch, cudaStream_t st, bool exact_class) {
+    if (a.n <= 0) return RN_OK;
+    static const int impl = [] { const char *e = getenv("RN_BP_IMPL"); return e ? atoi(e) : 4; }();
+    if (impl == 4 && exact_class && nch <= RN_BP3_MAX_NCH) {
+        switch (nch) {
+            case 1: return launch_bp4_n<1>(d, a, first_sweep, st);
+            case 2: return launch_bp4_n<2>(d, a, first_sweep, st);
+            case 3: return launch_bp4_n<3>(d, a, first_sweep, st);
+            case 4: return launch_bp4_n<4>(d, a, first_sweep, st);
+            case 5: return launch_bp4_n<5>(d, a, first_sweep, st);
+            case 6: return launch_bp4_n<6>(d, a, first_sweep, st);
+        }
+    }
+    static const int dbg = [] { const char *e = getenv("RN_BP_DEBUG"); return e ? atoi(e) : 0; }();
+    a.debug = dbg;
+    if (impl == 3 && nch <= RN_BP3_MAX_NCH) {
+        switch (nch) {
+            case 1: return launch_bp3_n<1>(d, a, first_sweep, st);
+            case 2: return launch_bp3_n<2>(d, a, first_sweep, st);
+            case 3: return launch_bp3_n<3>(d, a, first_sweep, st);
+            case 4: return launch_bp3_n<4>(d, a, first_sweep, st);
+            case 5: return launch_bp3_n<5>(d, a, first_sweep, st);
+            case 6: return launch_bp3_n<6>(d, a, first_sweep, st);
+        }
+    }
+    return launch_bp2<false>(d, a, first_sweep, nch, st);
 }
 
 template <bool kAos>
@@ -552,14 +617,14 @@ int rn_engine_bp_iteration(const RnParams *p, const int32_t *lin,
     a.acc_out = acc_out;
     if (!order || !class_offsets) {   // no binning: one launch sized for the longest ray
         a.first = 0; a.n = n_rays;
-        return launch_bp2<false>(d, a, first_sweep != 0, (max_count + RN_CHUNK - 1) / RN_CHUNK, S(stream));
+        return launch_bp_class(d, a, first_sweep != 0, (max_count + RN_CHUNK - 1) / RN_CHUNK, S(stream), false);
     }
     a.order = order;
     for (int c = 1; c < RN_NCLASS; c++) {   // class 0 (count <= 1) is skipped by BP
         a.first = class_offsets[c];
         a.n = class_offsets[c + 1] - class_offsets[c];
         if (a.first < 0 || a.n < 0 || a.first + a.n > n_rays) return fail(RN_ERR_SHAPE, "class_offsets out of range");
-        rc = launch_bp2<false>(d, a, first_sweep != 0, c, S(stream));
+        rc = launch_bp_class(d, a, first_sweep != 0, c, S(stream), true);
         if (rc) return rc;
     }
     return RN_OK;

@@ -1,0 +1,202 @@
+// rn_bp4.cuh -- one BP sweep (a5 + a6): register-resident rays (rn_bp3.cuh) + software prefetch.
+//
+// Measurements behind this version (B200, C3, non-first sweep; profiles/README.md):
+//   * the memory operations of a sweep alone (bp_memonly_kernel: row reads, gathers, message
+//     stores, REDs, no arithmetic) take 3.55 ms; rows only 2.36 ms; the REDs cost 1.0 ms and the
+//     gathers 0.26 ms on top of the rows;
+//   * bp3_kernel (same memory operations + arithmetic) takes 4.7 ms: with ~100 registers per
+//     thread only 16-20 warps fit on an SM and each of them alternates between "load the whole
+//     ray" and "compute", so a good part of the load latency is exposed.
+// Here every warp works through a run of consecutive rays and the rows of the NEXT ray travel to
+// shared memory with cp.async (16 bytes per lane, L2 evict-first, no L1 allocation, no registers)
+// while the current ray is computed; the message buffer doubles as the transposition scratch
+// between the lane-consecutive gather / RED layout and the 4-voxels-per-lane scan layout.
+//
+// Contract: every ray of the launch has exactly NCH chunks (rn_class_of(L) == NCH, guaranteed by
+// the binning) -- only the last chunk is masked.
+#pragma once
+
+#include "rn_bp3.cuh"
+
+__device__ __forceinline__ void rn_cp_async16(uint32_t dst_smem, const void *src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void rn_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void rn_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#ifndef RN_BP4_RAYS_PER_WARP
+#define RN_BP4_RAYS_PER_WARP 16
+#endif
+
+// shared memory of one warp: 2 x (lin, s_hat) + (kFirst ? 1 : 2) x msgs rows of NCH * 128 words
+__host__ __device__ constexpr int rn_bp4_warp_words(int nch, bool first) { return nch * RN_CHUNK * (first ? 5 : 6); }
+
+template <int NCH, bool kFirst>
+__global__ void __launch_bounds__(128) bp4_kernel(RnDev p, Bp2Args a) {
+    extern __shared__ __align__(16) unsigned char rn_bp4_smem[];
+    constexpr int ROW = NCH * RN_CHUNK;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float *base = reinterpret_cast<float *>(rn_bp4_smem) + (size_t)wid * rn_bp4_warp_words(NCH, kFirst);
+    // layout: lin[2][ROW], s_hat[2][ROW], msgs[kFirst ? 1 : 2][ROW]
+    const uint64_t pol_stream = rn_policy_evict_first();
+    const uint64_t pol_keep = rn_policy_evict_last();
+
+    // this warp's rays: positions k0 + 4 * t of the launch (the four warps of the CTA hold four
+    // consecutive entries of order[], i.e. neighbouring pixels, at any time)
+    const int64_t k0 = (int64_t)blockIdx.x * (4 * RN_BP4_RAYS_PER_WARP) + wid;
+    int nmine = 0;
+    if (k0 < a.n) nmine = (int)min((int64_t)RN_BP4_RAYS_PER_WARP, (a.n - k0 + 3) / 4);
+    if (nmine == 0) return;
+
+    auto ray_of = [&](int t) -> int64_t {
+        const int64_t k = k0 + 4 * (int64_t)t;
+        return a.order ? (int64_t)__ldg(a.order + a.first + k) : a.first + k;
+    };
+    auto prefetch = [&](int64_t r, int L, int b) {
+        const int32_t *lin_row = a.lin + r * (int64_t)p.row_stride;
+        const float *s_row = a.s_hat + r * (int64_t)p.row_stride;
+        const float *m_row = a.msgs + r * (int64_t)p.row_stride;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int i0 = c * RN_CHUNK + 4 * lane;
+            if (c < NCH - 1 || i0 < L) {
+                rn_cp_async16(rn_smem_u32(base + b * ROW + i0), lin_row + i0, pol_stream);
+                rn_cp_async16(rn_smem_u32(base + (2 + b) * ROW + i0), s_row + i0, pol_stream);
+                if (!kFirst) rn_cp_async16(rn_smem_u32(base + (4 + b) * ROW + i0), m_row + i0, pol_stream);
+            }
+        }
+        rn_cp_async_commit();
+    };
+
+    int64_t r_cur = ray_of(0);
+    int L_cur = __ldg(a.count + r_cur);
+    prefetch(r_cur, L_cur, 0);
+    int64_t r_nxt = 0;
+    int L_nxt = 0;
+    if (nmine > 1) { r_nxt = ray_of(1); L_nxt = __ldg(a.count + r_nxt); }
+
+    for (int t = 0; t < nmine; t++) {
+        const int b = t & 1;
+        const int64_t r = r_cur;
+        const int L = L_cur;
+        __syncwarp();   // every lane is done with the buffers of ray t - 1
+        if (t + 1 < nmine) {
+            prefetch(r_nxt, L_nxt, b ^ 1);
+            r_cur = r_nxt; L_cur = L_nxt;
+            if (t + 2 < nmine) { r_nxt = ray_of(t + 2); L_nxt = __ldg(a.count + r_nxt); }
+            rn_cp_async_wait<1>();
+        } else {
+            rn_cp_async_wait<0>();
+        }
+        __syncwarp();   // ... and every lane's copies of ray t have landed
+        const int *sLin = reinterpret_cast<const int *>(base + b * ROW);
+        const float *sS = base + (2 + b) * ROW;
+        float *sM = base + (4 + (kFirst ? 0 : b)) * ROW;
+        float *m_row = a.msgs + r * (int64_t)p.row_stride;
+
+        // ---- accumulator gathers, lane-consecutive (neighbouring lanes share sectors) -------------
+        float ga[NCH][4];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = c * RN_CHUNK + 32 * j + lane;
+                ga[c][j] = 0.f;
+                if (c < NCH - 1 || i < L) ga[c][j] = rn_ld_acc_pol(a.acc_in + sLin[i], pol_keep);
+            }
+        }
+
+        // ---- forward: occupancy-to-ray values, prefix scans ----------------------------------------
+        float w[NCH][4], cps[NCH][4], pre0[NCH], tot[NCH];
+        float carry_cp = 1.f, carry_pre = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int i0 = c * RN_CHUNK + 4 * lane;
+            const float4 s4 = *reinterpret_cast<const float4 *>(sS + i0);
+            float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);   // first sweep: messages are 0 (mrf_np.py:275)
+            if (!kFirst) m4 = *reinterpret_cast<const float4 *>(sM + i0);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; j++) sM[c * RN_CHUNK + 32 * j + lane] = ga[c][j];
+            __syncwarp();
+            const float4 acc4 = *reinterpret_cast<const float4 *>(sM + i0);
+            const float accv[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+            float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+            float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+            float o[4], q[4];
+            if (c == NCH - 1) {
+                // slots beyond the ray: s = 0 (nothing reaches the sums), message 0 (accumulator is 0 already)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool ok = i0 + j < L;
+                    sv[j] = ok ? sv[j] : 0.f;
+                    mv[j] = ok ? mv[j] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                w[c][j] = rn_occ_w2(accv[j], mv[j]);
+                rn_occ_from_w(w[c][j], o[j], q[j]);
+            }
+            // exclusive products cp_i = prod_{k<i} (1 - o_k)
+            const float lp0 = q[0], lp1 = lp0 * q[1], lp2 = lp1 * q[2], lp3 = lp2 * q[3];
+            const float inc = rn_warp_incl_scan_mul(lp3, lane);
+            float exc = __shfl_up_sync(RN_FULL_MASK, inc, 1);
+            if (lane == 0) exc = 1.f;
+            const float basecp = carry_cp * exc;
+            carry_cp = carry_cp * __shfl_sync(RN_FULL_MASK, inc, 31);
+            cps[c][0] = basecp * sv[0];
+            cps[c][1] = (basecp * lp0) * sv[1];
+            cps[c][2] = (basecp * lp1) * sv[2];
+            cps[c][3] = (basecp * lp2) * sv[3];
+            // prefix sums of a_i = o_i cp_i s_i (true exclusive scan: no cancellation)
+            const float la = fmaf(o[3], cps[c][3], fmaf(o[2], cps[c][2], fmaf(o[1], cps[c][1], o[0] * cps[c][0])));
+            const float sinc = rn_warp_incl_scan_add(la, lane);
+            float sexc = __shfl_up_sync(RN_FULL_MASK, sinc, 1);
+            if (lane == 0) sexc = 0.f;
+            tot[c] = __shfl_sync(RN_FULL_MASK, sinc, 31);
+            pre0[c] = carry_pre + sexc;
+            carry_pre += tot[c];
+        }
+
+        // ---- backward: suffix sums, messages, scatter-add ----------------------------------------------
+        float carry_suf = 0.f;
+#pragma unroll
+        for (int c = NCH - 1; c >= 0; c--) {
+            float o[4], q[4], av[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                rn_occ_from_w(w[c][j], o[j], q[j]);
+                av[j] = o[j] * cps[c][j];
+            }
+            const float ra3 = av[3], ra2 = av[2] + ra3, ra1 = av[1] + ra2, ra0 = av[0] + ra1;
+            // sum over the lanes ABOVE this one: shift, then inclusive reverse scan (exact exclusive)
+            float above = __shfl_down_sync(RN_FULL_MASK, ra0, 1);
+            if (lane == 31) above = 0.f;
+            const float sbase = carry_suf + rn_warp_incl_rscan_add(above, lane);
+            const float suf[4] = {sbase + ra1, sbase + ra2, sbase + ra3, sbase};
+            float pre = pre0[c];
+            float msg[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // p / (1 - p) = pos / neg, pos = pre + cp s, neg = pre + suf / q  ->  pos q / (pre q + suf)
+                const float pos = pre + cps[c][j];
+                const float den = fmaf(pre, q[j], suf[j]);
+                msg[j] = 0.6931471805599453f * rn_lg2((pos * q[j]) * rn_rcp(den));
+                pre += av[j];
+            }
+            carry_suf += tot[c];
+            const int i0 = c * RN_CHUNK + 4 * lane;
+            const float4 msg4 = make_float4(msg[0], msg[1], msg[2], msg[3]);
+            if (c < NCH - 1 || i0 < L) rn_st_stream4_pol(m_row + i0, msg4, pol_stream);   // rows hold whole quads
+            *reinterpret_cast<float4 *>(sM + i0) = msg4;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = c * RN_CHUNK + 32 * j + lane;
+                if (c < NCH - 1 || i < L) rn_red_add_pol(a.acc_out + sLin[i], sM[i], pol_keep);
+            }
+        }
+    }
+}

@@ -8,6 +8,7 @@
 #include "rn_kernels.cuh"
 #include "rn_bp3.cuh"
 #include "rn_bp4.cuh"
+#include "rn_simmap3.cuh"
 
 namespace {
 
@@ -124,6 +125,52 @@ int launch_simmap(const RnDev &d, SimMapArgs a, bool mapping, cudaStream_t st) {
     const int64_t blocks = (a.n_rays + warps - 1) / warps;
     simmap_kernel<kAos><<<(unsigned)blocks, warps * 32, smem, st>>>(d, a);
     return check_launch("simmap_kernel");
+}
+
+// Resident front end, F = 32 (rn_simmap3.cuh): similarity + softmax -> S_planes scratch, then
+// plane->voxel mapping -> s_hat, lin.
+struct PlaneScratch {
+    float *ptr = nullptr;
+    int64_t cap = 0;
+};
+thread_local PlaneScratch g_planes;
+
+int launch_simmap3(const RnDev &d, SimMapArgs a, cudaStream_t st) {
+    if (a.n_rays <= 0) return RN_OK;
+    const int64_t need = a.n_rays * (int64_t)d.D;
+    if (g_planes.cap < need) {
+        if (g_planes.ptr) cudaFree(g_planes.ptr);
+        cudaError_t e = cudaMalloc(&g_planes.ptr, sizeof(float) * (size_t)need);
+        if (e != cudaSuccess) { g_planes.ptr = nullptr; g_planes.cap = 0; return fail(RN_ERR_CUDA, "cudaMalloc plane scratch: %s", cudaGetErrorString(e)); }
+        g_planes.cap = need;
+    }
+    a.S_planes = g_planes.ptr;
+    a.val_stride = (int)row_stride_of(d.M);
+    a.tile_len = tile_len_for(d, a.n_rays);
+    { const char *m = getenv("RN_TILE_MODE"); a.tile_mode = m ? atoi(m) : 2; }
+    const size_t smem_a = sizeof(float) * (rn_simscore3_cta_words(d.V) + 4 * rn_simscore3_warp_words(d.D, d.V));
+    const size_t smem_b = sizeof(float) * (rn_planemap3_cta_words(d.gx + d.gy + d.gz) + 4 * rn_planemap3_warp_words(d.D, a.val_stride));
+    static thread_local size_t conf_b = 0;
+    if (smem_a > 48 * 1024) return fail(RN_ERR_UNSUPPORTED, "depth_planes x n_views too large for the similarity kernel's shared memory");
+    if (smem_b > 48 * 1024 && smem_b > conf_b) {
+        cudaError_t e = cudaFuncSetAttribute(planemap3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "planemap3 smem attribute: %s", cudaGetErrorString(e));
+        conf_b = smem_b;
+    }
+    const unsigned blocks_a = (unsigned)((a.n_rays + 3) / 4);
+    switch (d.V) {   // common view counts get fully unrolled loops
+        case 3: simscore3_kernel<3><<<blocks_a, 128, smem_a, st>>>(d, a); break;
+        case 5: simscore3_kernel<5><<<blocks_a, 128, smem_a, st>>>(d, a); break;
+        case 7: simscore3_kernel<7><<<blocks_a, 128, smem_a, st>>>(d, a); break;
+        case 9: simscore3_kernel<9><<<blocks_a, 128, smem_a, st>>>(d, a); break;
+        case 11: simscore3_kernel<11><<<blocks_a, 128, smem_a, st>>>(d, a); break;
+        default: simscore3_kernel<0><<<blocks_a, 128, smem_a, st>>>(d, a); break;
+    }
+    int rc = check_launch("simscore3_kernel");
+    if (rc) return rc;
+    const int64_t per_cta = 4 * RN_SM3_RAYS_PER_WARP;
+    planemap3_kernel<<<(unsigned)((a.n_rays + per_cta - 1) / per_cta), 128, smem_b, st>>>(d, a);
+    return check_launch("planemap3_kernel");
 }
 
 // One BP sweep over rays [a.first, a.first + a.n) of a.order (or of the ray array itself).
@@ -579,6 +626,8 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
     a.ray_idxs = ray_idxs; a.features = features; a.view_ids = view_ids; a.P = P; a.P_inv = P_inv; a.centre = centre;
     a.axes = axis_centres; a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.lin = lin;
     a.n_rays = n_rays;
+    static const int impl = [] { const char *e = getenv("RN_SIMMAP_IMPL"); return e ? atoi(e) : 3; }();
+    if (impl == 3 && d.F == 32) return launch_simmap3(d, a, S(stream));
     return launch_simmap<false>(d, a, true, S(stream));
 }
 

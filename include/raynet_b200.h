@@ -200,6 +200,20 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
                        float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *s_hat,
                        int32_t *lin, int64_t n_rays, void *stream);
 
+/* The two halves of rn_engine_frontend as separate calls, so that a caller can trace the rays of
+ * every reference image (no feature maps needed: sample_in_bbox + DDA -> starts, ends, ray_hdr,
+ * codes, count) and bin them while the feature maps are still on their way to the device, and run
+ * the similarity + plane->voxel mapping (-> s_hat, lin) afterwards.  starts / ends: float32 [n][3],
+ * written by the first call and read by the second.  Replaces the same reference code as
+ * rn_engine_frontend (raynet_fp.py:43-120 + forward_pass.py:622-663). */
+int rn_engine_trace(const RnParams *p, const int32_t *ray_idxs, const float *P_inv, const float *centre,
+                    float *starts, float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, int64_t n_rays,
+                    void *stream);
+int rn_engine_similarity(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
+                         const float *P, const float *axis_centres, const float *starts, const float *ends,
+                         const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count, float *s_hat,
+                         int32_t *lin, int64_t n_rays, void *stream);
+
 /* Group the rays by length class (class c = ceil(count / 128) for count >= 2, class 0 = the rays
  * BP skips) so that each class runs with the shared memory its rays need.  order: int32 [n]
  * out, the ray positions class by class; inside a class rays follow an 8x8-pixel tiled

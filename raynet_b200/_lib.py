@@ -68,6 +68,8 @@ SIGNATURES = {
     "rn_mvcnn_voxel": [_PP] + [_PTR] * 9 + [_I64, _PTR],
     "rn_mvcnn_voxel_depth": [_PP] + [_PTR] * 10 + [_I64, _PTR],
     "rn_engine_frontend": [_PP, _PTR, _PTR, _PTR, _I32] + [_PTR] * 11 + [_I64, _PTR],
+    "rn_engine_trace": [_PP] + [_PTR] * 8 + [_I64, _PTR],
+    "rn_engine_similarity": [_PP, _PTR, _PTR, _I32] + [_PTR] * 9 + [_I64, _PTR],
     "rn_engine_bin_rays": [_PP, _PTR, _I64, _I64, _PTR, _PTR, _PTR],
     "rn_engine_bp_iteration": [_PP] + [_PTR] * 8 + [_I32, _I32, _I64, _PTR],
     "rn_engine_depth": [_PP] + [_PTR] * 8 + [_I32, _PTR, _PTR, _I64, _PTR],

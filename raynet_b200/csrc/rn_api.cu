@@ -597,11 +597,24 @@ int rn_bricks_to_grid(const RnParams *p, const float *bricks, float *grid, int a
     return check_launch("bricks_to_grid_kernel");
 }
 
-int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *features,
-                       const int32_t *view_ids, int32_t n_feature_slots, const float *P,
-                       const float *P_inv, const float *centre, const float *axis_centres, float *starts,
-                       float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *s_hat,
-                       int32_t *lin, int64_t n_rays, void *stream) {
+int rn_engine_trace(const RnParams *p, const int32_t *ray_idxs, const float *P_inv, const float *centre,
+                    float *starts, float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, int64_t n_rays,
+                    void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, true);
+    if (rc) return rc;
+    if (n_rays <= 0) return RN_OK;
+    if (!starts || !ends) return fail(RN_ERR_SHAPE, "rn_engine_trace needs starts and ends buffers");
+    DdaCodesArgs da = {};
+    da.ray_idxs = ray_idxs; da.P_inv = P_inv; da.centre = centre; da.starts = starts; da.ends = ends;
+    da.hdr = ray_hdr; da.codes = codes; da.count = count; da.n_rays = n_rays;
+    return launch_dda_codes(d, da, S(stream));
+}
+
+int rn_engine_similarity(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
+                         const float *P, const float *axis_centres, const float *starts, const float *ends,
+                         const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count, float *s_hat,
+                         int32_t *lin, int64_t n_rays, void *stream) {
     RnDev d;
     int rc = make_dev(p, d, true, true, true);
     if (rc) return rc;
@@ -611,24 +624,35 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
         if ((int64_t)n_feature_slots * d.fh * d.fw * d.F >= (1ll << 31))
             return fail(RN_ERR_UNSUPPORTED, "feature volume too large for int32 element offsets");
     }
-    if ((starts == nullptr) != (ends == nullptr)) return fail(RN_ERR_SHAPE, "starts and ends must both be given or both NULL");
-    if (!starts) {
-        rc = ray_scratch(n_rays, &starts, &ends);
-        if (rc) return rc;
-    }
-    DdaCodesArgs da = {};
-    da.ray_idxs = ray_idxs; da.P_inv = P_inv; da.centre = centre; da.starts = starts; da.ends = ends;
-    da.hdr = ray_hdr; da.codes = codes; da.count = count; da.n_rays = n_rays;
-    rc = launch_dda_codes(d, da, S(stream));
-    if (rc) return rc;
+    if (!starts || !ends) return fail(RN_ERR_SHAPE, "rn_engine_similarity needs the starts / ends of rn_engine_trace");
     SimMapArgs a = {};
     a.starts_in = starts; a.ends_in = ends;
-    a.ray_idxs = ray_idxs; a.features = features; a.view_ids = view_ids; a.P = P; a.P_inv = P_inv; a.centre = centre;
+    a.features = features; a.view_ids = view_ids; a.P = P;
     a.axes = axis_centres; a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.lin = lin;
     a.n_rays = n_rays;
     static const int impl = [] { const char *e = getenv("RN_SIMMAP_IMPL"); return e ? atoi(e) : 3; }();
     if (impl == 3 && d.F == 32) return launch_simmap3(d, a, S(stream));
     return launch_simmap<false>(d, a, true, S(stream));
+}
+
+int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *features,
+                       const int32_t *view_ids, int32_t n_feature_slots, const float *P,
+                       const float *P_inv, const float *centre, const float *axis_centres, float *starts,
+                       float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *s_hat,
+                       int32_t *lin, int64_t n_rays, void *stream) {
+    if (n_rays <= 0) {
+        RnDev d;
+        return make_dev(p, d, true, true, true);
+    }
+    if ((starts == nullptr) != (ends == nullptr)) return fail(RN_ERR_SHAPE, "starts and ends must both be given or both NULL");
+    if (!starts) {
+        int rc = ray_scratch(n_rays, &starts, &ends);
+        if (rc) return rc;
+    }
+    int rc = rn_engine_trace(p, ray_idxs, P_inv, centre, starts, ends, ray_hdr, codes, count, n_rays, stream);
+    if (rc) return rc;
+    return rn_engine_similarity(p, features, view_ids, n_feature_slots, P, axis_centres, starts, ends, ray_hdr, codes,
+                                count, s_hat, lin, n_rays, stream);
 }
 
 int rn_engine_bin_rays(const RnParams *p, const int32_t *count, int64_t n_rays, int64_t seg_len, int32_t *order,

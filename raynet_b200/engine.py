@@ -73,6 +73,7 @@ class RayPotentialEngine(object):
         self.acc_prev = torch.full((self.GB,), self.prior, dtype=torch.float32, **kw)
         self.acc_new = torch.empty((self.GB,), dtype=torch.float32, **kw)
         self.axes = torch.zeros((sum(self.grid_shape),), dtype=torch.float32, **kw)
+        self.starts = self.ends = None   # float32 [capacity, 3], allocated by the first trace_image()
         self._class_scratch = torch.zeros((2 * self.n_classes,), dtype=torch.int64, **kw)
         self._class_offsets = None  # host int64 [n_classes + 1] (ctypes array) once rays are binned
         self.class_sizes = None
@@ -120,26 +121,45 @@ class RayPotentialEngine(object):
         """Front end for the rays `ray_idxs` (int32 device tensor, column-major pixel ids) of one
         reference image.  features: CUDA f32 tensor [V or slots, H+p+1, W+p+1, F]; P [V,3,4],
         P_inv [4,3], centre [4] CUDA f32 tensors.  Appends the rays to the resident state."""
+        k = self.trace_image(ray_idxs, P_inv, centre)
+        self.score_image(k, features, P, view_ids=view_ids, n_feature_slots=n_feature_slots)
+        if keep_start_end:
+            start, n, _ = self.segments[k]
+            return self.starts[start:start + n], self.ends[start:start + n]
+        return None
+
+    def trace_image(self, ray_idxs, P_inv, centre):
+        """First half of the front end (needs no feature maps): sample_in_bbox + DDA for the rays
+        of one reference image -> step codes, counts, ray start / end.  Returns the image's index."""
         assert self._axes_set, "call set_voxel_grid() first"
         n = int(ray_idxs.shape[0])
         start = self.n_rays
         if start + n > self.capacity:
             raise AssertionError("engine capacity exceeded: %d + %d > %d" % (start, n, self.capacity))
         sl = slice(start, start + n)
-        starts = ends = None
-        if keep_start_end:
-            starts = torch.empty((n, 3), dtype=torch.float32, device=self.dev)
-            ends = torch.empty((n, 3), dtype=torch.float32, device=self.dev)
-        slots = int(n_feature_slots if n_feature_slots is not None else features.shape[0])
-        _lib.call("rn_engine_frontend", self.params, _ptr(ray_idxs), _ptr(features),
-                  _ptr(view_ids) if view_ids is not None else None, slots, _ptr(P), _ptr(P_inv), _ptr(centre),
-                  _ptr(self.axes), _ptr(starts), _ptr(ends), _ptr(self.hdr[sl]), _ptr(self.codes[sl]),
-                  _ptr(self.count[sl]), _ptr(self.s_hat[sl]), _ptr(self.lin[sl]), n, current_stream_ptr())
-        self.launches += 2
+        if self.starts is None:
+            self.starts = torch.empty((self.capacity, 3), dtype=torch.float32, device=self.dev)
+            self.ends = torch.empty((self.capacity, 3), dtype=torch.float32, device=self.dev)
+        _lib.call("rn_engine_trace", self.params, _ptr(ray_idxs), _ptr(P_inv), _ptr(centre), _ptr(self.starts[sl]),
+                  _ptr(self.ends[sl]), _ptr(self.hdr[sl]), _ptr(self.codes[sl]), _ptr(self.count[sl]), n,
+                  current_stream_ptr())
+        self.launches += 1
         self.segments.append((start, n, centre))
         self.n_rays = start + n
         self._class_offsets = None
-        return (starts, ends) if keep_start_end else None
+        return len(self.segments) - 1
+
+    def score_image(self, k, features, P, view_ids=None, n_feature_slots=None):
+        """Second half of the front end for image k of trace_image(): plane-sweep similarity +
+        plane->voxel mapping -> s_hat, lin rows."""
+        start, n, _ = self.segments[k]
+        sl = slice(start, start + n)
+        slots = int(n_feature_slots if n_feature_slots is not None else features.shape[0])
+        _lib.call("rn_engine_similarity", self.params, _ptr(features), _ptr(view_ids) if view_ids is not None else None,
+                  slots, _ptr(P), _ptr(self.axes), _ptr(self.starts[sl]), _ptr(self.ends[sl]), _ptr(self.hdr[sl]),
+                  _ptr(self.codes[sl]), _ptr(self.count[sl]), _ptr(self.s_hat[sl]), _ptr(self.lin[sl]), n,
+                  current_stream_ptr())
+        self.launches += 2
 
     def finalize_frontend(self):
         """Bin the rays by length class (one small device->host read of the class sizes, so

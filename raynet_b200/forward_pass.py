@@ -203,6 +203,8 @@ class RayNetForwardPass(ForwardPass):
         self.engine = None
         self._de = None
         self._feat_dev = None
+        self._copy_stream = None
+        self._staging = {}
         self.h2d_bytes = 0                      # bytes copied host->device / device->host by the last
         self.d2h_bytes = 0                      # forward_pass() call (bench.py's e2e accounting)
 
@@ -216,6 +218,29 @@ class RayNetForwardPass(ForwardPass):
                 self._generation_params.neighbors + 1, feature_size, scene.image_shape[0], scene.image_shape[1],
                 self._generation_params.padding, scene.bbox.ravel(), grid_shape, self._sampling_scheme)
         return [self._fp, self._de]
+
+    def _pinned(self, name, shape, dtype):
+        """A cached pinned host staging buffer."""
+        buf = self._staging.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(shape, dtype=dtype).pin_memory()
+            self._staging[name] = buf
+        return buf
+
+    def _ray_ids(self, ray_idxs, n_pixels, dev, k=0):
+        """Device int32 ray ids.  The usual case -- every pixel of the image is a ray
+        (forward_pass.py:168-179 without filtering) -- is generated on the device once and cached;
+        filtered ray sets are uploaded through a pinned buffer."""
+        if len(ray_idxs) == n_pixels and (n_pixels == 0 or (int(ray_idxs[0]) == 0 and int(ray_idxs[-1]) == n_pixels - 1)):
+            ids = self._staging.get("all_pixels")
+            if ids is None or ids.shape[0] != n_pixels:
+                ids = torch.arange(n_pixels, dtype=torch.int32, device=dev)
+                self._staging["all_pixels"] = ids
+            return ids
+        host = self._pinned("ray_ids_%d" % k, (len(ray_idxs),), torch.int32)   # one buffer per image: copies are asynchronous
+        host.numpy()[:] = ray_idxs
+        self.h2d_bytes += host.numel() * 4
+        return host.to(dev, non_blocking=True)
 
     def _make_engine(self, scene, F, n_rays_total):
         gp = self._generation_params
@@ -258,27 +283,52 @@ class RayNetForwardPass(ForwardPass):
         f_host = self._view_features(scene, views)
         if self._feat_dev is None or self._feat_dev.shape != f_host.shape:
             self._feat_dev = torch.empty(f_host.shape, dtype=torch.float32, device=dev)
-        self._feat_dev.copy_(f_host, non_blocking=True)
+        # the feature maps travel on a copy stream while the rays are traced and binned (neither
+        # needs them); the similarity kernels wait for the copy
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        self._copy_stream.wait_stream(main)      # the previous call's readers of _feat_dev are done
+        with torch.cuda.stream(self._copy_stream):
+            self._feat_dev.copy_(f_host, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record()
         self.h2d_bytes += f_host.numel() * 4
         if self.engine is None or self.engine.capacity < total:
             self.engine = self._make_engine(scene, f_host.shape[-1], total)
         else:
             self.engine.reset()
-        # ---- front end per reference image -----------------------------------------------------
+        # ---- front end, first half: trace the rays of every reference image, bin them ----------
+        # all camera matrices and view slots travel in ONE pinned buffer (pageable uploads block the
+        # host for ~0.5 ms each and would leave the GPU idle between the per-image launches)
+        n_img = len(img_ids)
+        nV = len(orders[0])
+        stride = 12 * nV + 16
+        meta = self._pinned("cams", (n_img, stride), torch.float32)
+        vids = self._pinned("view_ids", (n_img, nV), torch.int32)
         for k, ref_idx in enumerate(img_ids):
             images = scene.get_image_with_neighbors(ref_idx)
-            cam = np.concatenate([np.array([im.camera.P for im in images], dtype=np.float32).ravel(),
-                                  np.asarray(images[0].camera.P_pinv, dtype=np.float32).ravel(),
-                                  np.asarray(images[0].camera.center, dtype=np.float32).ravel()])
-            cam_dev = torch.from_numpy(cam).to(dev, non_blocking=True)
-            nP = 12 * len(images)
-            ids = torch.from_numpy(np.ascontiguousarray(rays[k], dtype=np.int32)).to(dev, non_blocking=True)
-            view_ids = torch.tensor([slot[v] for v in orders[k]], dtype=torch.int32).to(dev, non_blocking=True)
-            self.h2d_bytes += cam.nbytes + ids.numel() * 4 + view_ids.numel() * 4
-            self.engine.add_image(ids, self._feat_dev, cam_dev[:nP], cam_dev[nP:nP + 12], cam_dev[nP + 12:nP + 16],
-                                  view_ids=view_ids, n_feature_slots=len(views))
+            assert len(images) == nV
+            row = meta[k].numpy()
+            row[:12 * nV] = np.array([im.camera.P for im in images], dtype=np.float32).ravel()
+            row[12 * nV:12 * nV + 12] = np.asarray(images[0].camera.P_pinv, dtype=np.float32).ravel()
+            row[12 * nV + 12:] = np.asarray(images[0].camera.center, dtype=np.float32).ravel()[:4]
+            vids[k] = torch.tensor([slot[v] for v in orders[k]], dtype=torch.int32)
+        meta_dev = meta.to(dev, non_blocking=True)
+        vids_dev = vids.to(dev, non_blocking=True)
+        self.h2d_bytes += meta.numel() * 4 + vids.numel() * 4
+        per_image = []
+        for k, ref_idx in enumerate(img_ids):
+            ids = self._ray_ids(rays[k], H * W, dev, k)
+            nP = 12 * nV
+            self.engine.trace_image(ids, meta_dev[k, nP:nP + 12], meta_dev[k, nP + 12:nP + 16])
+            per_image.append((meta_dev[k, :nP], vids_dev[k]))
         self.engine.finalize_frontend()
         self.d2h_bytes += 4
+        # ---- front end, second half: similarity + plane->voxel mapping per reference image -----
+        main.wait_event(copied)
+        for k, (P_dev, view_ids) in enumerate(per_image):
+            self.engine.score_image(k, self._feat_dev, P_dev, view_ids=view_ids, n_feature_slots=len(views))
         # ---- BP sweeps + depth -----------------------------------------------------------------
         self.engine.run_bp(self.bp_iterations)
         depth = self.engine.depth().cpu().numpy()

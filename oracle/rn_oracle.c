@@ -24,8 +24,11 @@
  *   - planes->voxels: reference numpy li / li_2 (oracle/_ref/ref_planes_voxels_mapping*.so),
  *     the cross-check of tests/test_planes_voxels_mapping.py:61-78.
  *   - sample_in_bbox, similarity, arg-max depth have NO CPU twin and no test in the
- *     reference: these are restated from the .cu text only ("parity unpinned" for those
- *     three functions; their geometric properties are tested instead).
+ *     reference: they are restated from the .cu text and pinned on the GPU box against an
+ *     EXECUTION of the reference's own CUDA kernels (oracle/build_ref_cuda.py compiles
+ *     cuda_implementations/*.cu + the kernel text of raynet_fp.py for sm_100a,
+ *     tests/test_gpu_ref_cuda.py runs them next to the sm_100a kernels and this oracle's
+ *     outputs: voxel lists identical, distributions / messages / S_new within 1e-5).
  */
 #include <float.h>
 #include <math.h>

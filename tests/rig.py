@@ -52,6 +52,11 @@ def case_long(**kw):
     return Case(200, 3, 16, 32, 32, 600, n_rays=600, **kw)
 
 
+def case_nine(**kw):
+    """Nine views / 64 planes (the headline's view and plane counts) on a small image and grid."""
+    return Case(64, 9, 64, 40, 40, 192, n_rays=1000, **kw)
+
+
 def sigmoid(x):
     x = np.asarray(x, np.float64)
     return 1.0 / (1.0 + np.exp(-x))

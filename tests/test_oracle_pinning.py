@@ -232,3 +232,22 @@ def test_voxel_grid_table_is_separable(oracle):
         assert np.array_equal(vg[2], np.broadcast_to(vg[2, :1, :1, :], vg[2].shape))
     vg = get_voxel_grid([-1, -1, -1, 1, 1, 1], [32, 16, 8]).transpose(1, 2, 3, 0)
     assert np.array_equal(vg, oracle.voxel_grid(np.array([-1, -1, -1, 1, 1, 1], np.float32), [32, 16, 8]))
+
+
+def test_reference_cuda_kernels_compile_for_sm100a():
+    """oracle/build_ref_cuda.py: the reference's own .cu templates + the kernel text of raynet_fp.py,
+    substituted like PyCUDA's SourceModule would, compile with nvcc for sm_100a and export both fused
+    kernels (the GPU-side oracle of tests/test_gpu_ref_cuda.py).  Needs /root/reference and nvcc."""
+    import os
+    import shutil
+    import subprocess
+    from oracle import build_ref_cuda
+    if not os.path.isdir("/root/reference/raynet") or shutil.which("nvcc") is None:
+        pytest.skip("reference tree or nvcc absent")
+    assert build_ref_cuda.build()
+    for name in build_ref_cuda.CONFIGS:
+        cubin = os.path.join(build_ref_cuda.OUT, "raynet_fp_%s.cubin" % name)
+        assert os.path.exists(cubin)
+    out = subprocess.run(["cuobjdump", "-elf", os.path.join(build_ref_cuda.OUT, "raynet_fp_c1.cubin")],
+                         capture_output=True, text=True).stdout
+    assert ".text.batch_raynet_fp" in out and ".text.batch_complete_depth_estimation" in out

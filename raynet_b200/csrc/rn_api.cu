@@ -164,6 +164,7 @@ int launch_simmap3(const RnDev &d, SimMapArgs a, cudaStream_t st) {
         case 7: simscore3_kernel<7><<<blocks_a, 128, smem_a, st>>>(d, a); break;
         case 9: simscore3_kernel<9><<<blocks_a, 128, smem_a, st>>>(d, a); break;
         case 11: simscore3_kernel<11><<<blocks_a, 128, smem_a, st>>>(d, a); break;
+        case 15: simscore3_kernel<15><<<blocks_a, 128, smem_a, st>>>(d, a); break;
         default: simscore3_kernel<0><<<blocks_a, 128, smem_a, st>>>(d, a); break;
     }
     int rc = check_launch("simscore3_kernel");

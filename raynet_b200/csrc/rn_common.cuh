@@ -17,7 +17,7 @@
 #define RN_FULL_MASK 0xffffffffu
 #define RN_VOX_PER_LANE 4                       // consecutive voxels owned by one lane
 #define RN_CHUNK (32 * RN_VOX_PER_LANE)         // voxels one warp covers per chunk (128)
-#define RN_MAX_NCH 8                            // register-resident ray length = 8 * 128 = 1024 voxels
+#define RN_MAX_NCH 12                           // longest resident ray = 12 * 128 = 1536 voxels (C5: 3 x 512)
 
 // Device-side parameter block derived from RnParams on the host (rn_api.cu: make_dev).
 struct RnDev {

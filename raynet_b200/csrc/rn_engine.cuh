@@ -27,7 +27,7 @@
 
 #include "rn_common.cuh"
 
-#define RN_NCLASS 9   // class c = ceil(count / 128) for count >= 2 (1..8); class 0 = rays BP skips
+#define RN_NCLASS (RN_MAX_NCH + 1)   // class c = ceil(count / 128) for count >= 2 (1..RN_MAX_NCH); class 0 = rays BP skips
 
 // ---- brick layout -----------------------------------------------------------------------
 __host__ __device__ __forceinline__ int rn_brick_fx(const RnDev &p, int x) {

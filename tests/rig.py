@@ -52,6 +52,12 @@ def case_long(**kw):
     return Case(200, 3, 16, 32, 32, 600, n_rays=600, **kw)
 
 
+def case_xlong(**kw):
+    """C5's kernel parameters (15 views, 128 planes, M = 1536) on a small image: an elongated grid
+    whose rays along x cross ~1100 voxels, i.e. 9-10 chunks of 128 (the longest length classes)."""
+    return Case(None, 15, 128, 32, 32, 1536, n_rays=400, grid=(1000, 96, 96), **kw)
+
+
 def case_nine(**kw):
     """Nine views / 64 planes (the headline's view and plane counts) on a small image and grid."""
     return Case(64, 9, 64, 40, 40, 192, n_rays=1000, **kw)

@@ -32,7 +32,7 @@ def test_library_exports_every_header_symbol():
     # and the ctypes table covers the header exactly
     assert sorted(list(_lib.SIGNATURES) + _lib.OTHER_SYMBOLS) == syms
     assert lib.rn_abi_version() == 2
-    assert lib.rn_row_stride(96) == 128 and lib.rn_row_stride(768) == 768 and lib.rn_num_classes() == 9
+    assert lib.rn_row_stride(96) == 128 and lib.rn_row_stride(768) == 768 and lib.rn_num_classes() == 13
     assert lib.rn_code_stride(768) == 192 and lib.rn_code_stride(96) == 32 and lib.rn_code_stride(1) == 32
 
 

@@ -11,7 +11,7 @@ Gates (BASELINE.json north_star / SURVEY.md 8d):
 import numpy as np
 import pytest
 
-from rig import Case, case_c1, case_long, case_nine, case_small, sigmoid
+from rig import Case, case_c1, case_long, case_nine, case_small, case_xlong, sigmoid
 
 pytestmark = pytest.mark.gpu
 
@@ -422,7 +422,7 @@ def _run_engine(torch, c, iters, refs=None):
     return eng
 
 
-@pytest.mark.parametrize("mk,iters", [(case_c1, 3), (case_small, 3), (case_long, 2), (case_nine, 2)])
+@pytest.mark.parametrize("mk,iters", [(case_c1, 3), (case_small, 3), (case_long, 2), (case_nine, 2), (case_xlong, 2)])
 def test_engine_end_to_end_vs_oracle(torch_cuda, oracle, mk, iters):
     """C1 (and a longer-ray case) through the resident pipeline: every view a reference view in
     turn, I sweeps, depth pass -- against the oracle run the same way."""

@@ -211,7 +211,7 @@ int launch_bp3_n(const RnDev &d, const Bp2Args &a, bool first_sweep, cudaStream_
 
 // Prefetching register-resident sweep (rn_bp4.cuh); every ray of the launch has exactly NCH chunks.
 template <int NCH, bool kFirst>
-int launch_bp4_nf(const RnDev &d, const Bp2Args &a, cudaStream_t st) {
+int launch_bp4_nf(const RnDev &d, Bp2Args a, cudaStream_t st) {
     const size_t smem = (size_t)4 * rn_bp4_warp_words(NCH, kFirst) * sizeof(float);
     static thread_local bool configured = false;
     if (!configured) {
@@ -219,7 +219,9 @@ int launch_bp4_nf(const RnDev &d, const Bp2Args &a, cudaStream_t st) {
         if (e != cudaSuccess) return fail(RN_ERR_CUDA, "bp4 smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    const int per_cta = 4 * RN_BP4_RAYS_PER_WARP;
+    static const int rpw = [] { const char *e = getenv("RN_BP4_RPW"); int v = e ? atoi(e) : RN_BP4_RAYS_PER_WARP; return v > 0 ? v : RN_BP4_RAYS_PER_WARP; }();
+    a.rays_per_warp = rpw;
+    const int per_cta = 4 * rpw;
     const unsigned blocks = (unsigned)((a.n + per_cta - 1) / per_cta);
     bp4_kernel<NCH, kFirst><<<blocks, 128, smem, st>>>(d, a);
     return check_launch("bp4_kernel");

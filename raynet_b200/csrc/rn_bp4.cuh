@@ -26,7 +26,7 @@ template <int N>
 __device__ __forceinline__ void rn_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 #ifndef RN_BP4_RAYS_PER_WARP
-#define RN_BP4_RAYS_PER_WARP 16
+#define RN_BP4_RAYS_PER_WARP 8
 #endif
 
 // shared memory of one warp: 2 x (lin, s_hat) + (kFirst ? 1 : 2) x msgs rows of NCH * 128 words
@@ -44,9 +44,10 @@ __global__ void __launch_bounds__(128) bp4_kernel(RnDev p, Bp2Args a) {
 
     // this warp's rays: positions k0 + 4 * t of the launch (the four warps of the CTA hold four
     // consecutive entries of order[], i.e. neighbouring pixels, at any time)
-    const int64_t k0 = (int64_t)blockIdx.x * (4 * RN_BP4_RAYS_PER_WARP) + wid;
+    const int rpw = a.rays_per_warp;
+    const int64_t k0 = (int64_t)blockIdx.x * (4 * rpw) + wid;
     int nmine = 0;
-    if (k0 < a.n) nmine = (int)min((int64_t)RN_BP4_RAYS_PER_WARP, (a.n - k0 + 3) / 4);
+    if (k0 < a.n) nmine = (int)min((int64_t)rpw, (a.n - k0 + 3) / 4);
     if (nmine == 0) return;
 
     auto ray_of = [&](int t) -> int64_t {

@@ -252,6 +252,43 @@ def reference_cuda_bar(cfg, scene, model, my_views, dev):
                       "host loop and transfers of forward_pass.py excluded" % (n_img, n, t_fp, t_de, I)}
 
 
+def cnn_bar(cfg, dev, n_views):
+    """the MV-CNN (raynet_b200.models.SimpleCNN, 5 x conv3x3(32) + BN, fp32 CUDA cores)
+    on this rank's views, zero-padded images resident on the device; not part of `value` (the metric takes
+    feature volumes as inputs)."""
+    import torch
+    from raynet_b200.models import SimpleCNN
+    H, W = cfg["H"], cfg["W"]
+    model = SimpleCNN.random_init(channels=3, seed=0)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(7)
+    X = torch.zeros((n_views, H + 2 * PADDING, W + 2 * PADDING, 3), dtype=torch.float32)
+    X[:, PADDING:PADDING + H, PADDING:PADDING + W, :] = torch.rand((n_views, H, W, 3), generator=g)
+    X = X.to(dev)
+    for _ in range(2):
+        model.predict_device(X)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    reps = 5
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(reps):
+        out = model.predict_device(X)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / reps
+    flops, h, w, cin = 0.0, H + 2 * PADDING, W + 2 * PADDING, 3
+    for _ in range(5):
+        h, w = h - 2, w - 2
+        flops += 2.0 * n_views * h * w * 9 * cin * 32
+        cin = 32
+    sm_clock = torch.cuda.get_device_properties(dev).clock_rate * 1e3 if hasattr(torch.cuda.get_device_properties(dev), "clock_rate") else 1.965e9
+    peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * sm_clock / 1e12
+    return {"ms": ms, "views": n_views, "output_shape": list(out.shape), "tflops": flops / (ms * 1e-3) / 1e12,
+            "fp32_peak_tflops_nominal": peak, "frac": flops / (ms * 1e-3) / 1e12 / peak, "launches": 5,
+            "what": "5 x (conv3x3 -> 32 channels + folded batch norm [+ ReLU]) on %d zero-padded %dx%dx3 views, fp32 FMA "
+                    "pipe; peak = SMs x 128 FMA x 2 x max SM clock" % (n_views, H + 2 * PADDING, W + 2 * PADDING)}
+
+
 def run_reference_arm(args, cfg):
     """--impl reference: the CPU implementation on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -434,6 +471,13 @@ def run_gpu_arm(args, cfg):
             gpu_ref = reference_cuda_bar(cfg, scene, model, my_views, dev)
         except Exception as e:      # a reported extra, never a reason to lose the bench line
             gpu_ref = {"unavailable": repr(e)}
+    cnn = None
+    if rank == 0 and not args.no_cpu:
+        torch.cuda.empty_cache()
+        try:
+            cnn = cnn_bar(cfg, dev, len(my_views))
+        except Exception as e:
+            cnn = {"unavailable": repr(e)}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -473,6 +517,8 @@ def run_gpu_arm(args, cfg):
         }
         if gpu_ref is not None:
             line["gpu_reference"] = gpu_ref
+        if cnn is not None:
+            line["cnn"] = cnn
         if world == 1 and not args.no_cpu:
             from oracle import oracle as orc
             orc.build()

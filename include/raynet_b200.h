@@ -200,6 +200,19 @@ int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *
                        float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *s_hat,
                        int32_t *lin, int64_t n_rays, void *stream);
 
+/* SURVEY.md 8(f) row 1 -- the MV-CNN feature extractor in front of the path (models.py:90-111,
+ * forward_pass.py:181-198): one 'valid' 3x3 convolution to 32 channels with the inference-mode batch
+ * normalisation folded into a per-channel affine map, optional ReLU; channels-last float32.
+ *   in      [n_images][height][width][channels_in]        (channels_in = 1, 3 or 32)
+ *   weights [3][3][channels_in][32]                       (Keras Conv2D kernel layout)
+ *   out     [n_images][height-2][width-2][32] = relu?(scale[c] * conv(in)[c] + shift[c])
+ * with scale = gamma / sqrt(var + eps), shift = beta + scale * (bias - mean).  Five calls (the last
+ * without ReLU) on views zero-padded by 11 pixels give the [V][H+12][W+12][32] feature volume that
+ * rn_engine_similarity / rn_raynet_fp read. */
+int rn_conv3x3_bn_relu(const float *in, const float *weights, const float *scale, const float *shift, float *out,
+                       int32_t n_images, int32_t height, int32_t width, int32_t channels_in, int32_t relu,
+                       void *stream);
+
 /* The two halves of rn_engine_frontend as separate calls, so that a caller can trace the rays of
  * every reference image (no feature maps needed: sample_in_bbox + DDA -> starts, ends, ray_hdr,
  * codes, count) and bin them while the feature maps are still on their way to the device, and run

@@ -9,6 +9,7 @@
 #include "rn_bp3.cuh"
 #include "rn_bp4.cuh"
 #include "rn_simmap3.cuh"
+#include "rn_cnn.cuh"
 
 namespace {
 
@@ -172,6 +173,27 @@ int launch_simmap3(const RnDev &d, SimMapArgs a, cudaStream_t st) {
     const int64_t per_cta = 4 * RN_SM3_RAYS_PER_WARP;
     planemap3_kernel<<<(unsigned)((a.n_rays + per_cta - 1) / per_cta), 128, smem_b, st>>>(d, a);
     return check_launch("planemap3_kernel");
+}
+
+// one conv + folded BN (+ ReLU) layer of the MV-CNN (rn_cnn.cuh)
+template <int CIN>
+int launch_conv3x3(const ConvArgs &a, cudaStream_t st) {
+    const size_t smem = sizeof(float) * rn_cnn_smem_words<CIN>();
+    static thread_local bool configured = false;
+    static thread_local int sms = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int dev = 0;
+        if (e == cudaSuccess) e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "conv3x3 setup: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int ho = a.hi - 2, wo = a.wi - 2;
+    const int64_t tiles = (int64_t)a.n * ((ho + RN_CNN_TH - 1) / RN_CNN_TH) * ((wo + RN_CNN_TW - 1) / RN_CNN_TW);
+    const int64_t resident = (int64_t)sms * (smem > 100 * 1024 ? 1 : 2);   // persistent CTAs: one wave
+    conv3x3_kernel<CIN><<<(unsigned)(tiles < resident ? tiles : resident), 128, smem, st>>>(a);
+    return check_launch("conv3x3_kernel");
 }
 
 // One BP sweep over rays [a.first, a.first + a.n) of a.order (or of the ray array itself).
@@ -454,6 +476,22 @@ int rn_depth_estimate(const RnParams *p, const float *S_in, const int32_t *ray_v
     a.s_hat = S_in; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc = acc; a.msgs = msgs;
     a.S_new = S_new; a.n_rays = n_rays;
     return launch_depth2<true>(d, a, S(stream));
+}
+
+int rn_conv3x3_bn_relu(const float *in, const float *weights, const float *scale, const float *shift, float *out,
+                       int32_t n_images, int32_t height, int32_t width, int32_t channels_in, int32_t relu,
+                       void *stream) {
+    if (n_images <= 0) return RN_OK;
+    if (height < 3 || width < 3) return fail(RN_ERR_SHAPE, "conv3x3 needs images of at least 3 x 3 pixels");
+    if (!in || !weights || !scale || !shift || !out) return fail(RN_ERR_SHAPE, "conv3x3: NULL buffer");
+    if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return fail(RN_ERR_SHAPE, "conv3x3: output must be 16-byte aligned");
+    ConvArgs a = {in, weights, scale, shift, out, n_images, height, width, relu};
+    switch (channels_in) {
+        case 1: return launch_conv3x3<1>(a, S(stream));
+        case 3: return launch_conv3x3<3>(a, S(stream));
+        case 32: return launch_conv3x3<32>(a, S(stream));
+    }
+    return fail(RN_ERR_UNSUPPORTED, "conv3x3: %d input channels (supported: 1, 3, 32)", channels_in);
 }
 
 int rn_occupancy(const float *acc, float *out, int64_t n, void *stream) {

@@ -281,19 +281,26 @@ class RayNetForwardPass(ForwardPass):
         views = sorted(set(v for o in orders for v in o))
         slot = dict((v, k) for k, v in enumerate(views))
         f_host = self._view_features(scene, views)
-        if self._feat_dev is None or self._feat_dev.shape != f_host.shape:
-            self._feat_dev = torch.empty(f_host.shape, dtype=torch.float32, device=dev)
-        # the feature maps travel on a copy stream while the rays are traced and binned (neither
-        # needs them); the similarity kernels wait for the copy
-        if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
-        self._copy_stream.wait_stream(main)      # the previous call's readers of _feat_dev are done
-        with torch.cuda.stream(self._copy_stream):
-            self._feat_dev.copy_(f_host, non_blocking=True)
+        if f_host.is_cuda:
+            # the model produced the feature volume on the device (raynet_b200.models.SimpleCNN): nothing to upload
+            self._feat_dev = f_host.contiguous()
             copied = torch.cuda.Event()
-            copied.record()
-        self.h2d_bytes += f_host.numel() * 4
+            copied.record(main)
+            self.h2d_bytes += int(getattr(self._model, "last_h2d_bytes", 0))
+        else:
+            if self._feat_dev is None or self._feat_dev.shape != f_host.shape:
+                self._feat_dev = torch.empty(f_host.shape, dtype=torch.float32, device=dev)
+            # the feature maps travel on a copy stream while the rays are traced and binned (neither
+            # needs them); the similarity kernels wait for the copy
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_stream.wait_stream(main)      # the previous call's readers of _feat_dev are done
+            with torch.cuda.stream(self._copy_stream):
+                self._feat_dev.copy_(f_host, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record()
+            self.h2d_bytes += f_host.numel() * 4
         if self.engine is None or self.engine.capacity < total:
             self.engine = self._make_engine(scene, f_host.shape[-1], total)
         else:

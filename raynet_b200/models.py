@@ -1,0 +1,127 @@
+"""The MV-CNN feature extractor in front of the hot path.
+
+Mirror of the reference's `create_simple_cnn` (raynet/models.py:90-111): five
+`Conv2D(filters=32, kernel_size=3)` ('valid' padding, channels-last) each followed by
+`BatchNormalization`, with `Activation("relu")` after the first four.  Views are zero-padded by
+`padding` = 11 pixels first (forward_pass.py:181-198), so an (H, W) image gives an
+(H + 12, W + 12, 32) feature map.  The object offers the two calls the forward passes use:
+`predict(X)` like the Keras model (numpy in, numpy out) and `predict_features(scene, views)`, the
+hook of RayNetForwardPass that leaves the feature volume ON THE DEVICE (no 316 MB host round trip
+per call on the headline configuration).
+
+Compute: raynet_b200/csrc/rn_cnn.cuh through `rn_conv3x3_bn_relu` (one launch per layer).  There is
+no CPU fallback; weights come from `set_weights` in the Keras order (kernel, bias, gamma, beta,
+moving_mean, moving_variance per layer) or from `random_init` (no checkpoints are available offline).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .cuda_implementations.utils import current_stream_ptr, device
+
+BN_EPSILON = 1e-3      # keras.layers.BatchNormalization default
+
+
+class SimpleCNN(object):
+    n_layers = 5
+    filters = 32
+
+    def __init__(self, channels=3, epsilon=BN_EPSILON):
+        self.channels = int(channels)
+        self.epsilon = float(epsilon)
+        self._layers = None       # list of dict(kernel, bias, gamma, beta, mean, var) numpy float32
+        self._dev = None          # list of (kernel, scale, shift) CUDA tensors
+        self.launches = 0
+        self.last_h2d_bytes = 0   # bytes of zero-padded images uploaded by the last predict_features()
+
+    # ------------------------------------------------------------------ weights
+    @classmethod
+    def random_init(cls, channels=3, seed=0, trained_like=True):
+        """Glorot-uniform kernels (Keras default); with trained_like=True the batch-norm statistics and
+        biases are random too, so that every term of the folded affine map is exercised."""
+        rng = np.random.default_rng(seed)
+        m = cls(channels)
+        weights = []
+        cin = m.channels
+        for _ in range(cls.n_layers):
+            limit = np.sqrt(6.0 / (9 * cin + 9 * cls.filters))
+            weights.append(rng.uniform(-limit, limit, size=(3, 3, cin, cls.filters)).astype(np.float32))
+            if trained_like:
+                weights += [rng.normal(0, 0.05, cls.filters).astype(np.float32), rng.uniform(0.5, 1.5, cls.filters).astype(np.float32),
+                            rng.normal(0, 0.1, cls.filters).astype(np.float32), rng.normal(0, 0.1, cls.filters).astype(np.float32),
+                            rng.uniform(0.5, 1.5, cls.filters).astype(np.float32)]
+            else:
+                weights += [np.zeros(cls.filters, np.float32), np.ones(cls.filters, np.float32), np.zeros(cls.filters, np.float32),
+                            np.zeros(cls.filters, np.float32), np.ones(cls.filters, np.float32)]
+            cin = cls.filters
+        m.set_weights(weights)
+        return m
+
+    def set_weights(self, weights):
+        """Keras order: per layer kernel [3,3,Cin,32], bias, gamma, beta, moving_mean, moving_variance."""
+        assert len(weights) == 6 * self.n_layers
+        layers = []
+        cin = self.channels
+        for l in range(self.n_layers):
+            k, b, g, be, mu, var = [np.asarray(w, dtype=np.float32) for w in weights[6 * l:6 * l + 6]]
+            assert k.shape == (3, 3, cin, self.filters), k.shape
+            layers.append(dict(kernel=k, bias=b, gamma=g, beta=be, mean=mu, var=var))
+            cin = self.filters
+        self._layers = layers
+        self._dev = None
+
+    def get_weights(self):
+        out = []
+        for L in self._layers:
+            out += [L["kernel"], L["bias"], L["gamma"], L["beta"], L["mean"], L["var"]]
+        return out
+
+    def _device_weights(self):
+        if self._dev is None:
+            dev = device()
+            self._dev = []
+            for L in self._layers:
+                scale = L["gamma"].astype(np.float64) / np.sqrt(L["var"].astype(np.float64) + self.epsilon)
+                shift = L["beta"].astype(np.float64) + scale * (L["bias"].astype(np.float64) - L["mean"].astype(np.float64))
+                self._dev.append((torch.from_numpy(np.ascontiguousarray(L["kernel"])).to(dev),
+                                  torch.from_numpy(scale.astype(np.float32)).to(dev),
+                                  torch.from_numpy(shift.astype(np.float32)).to(dev)))
+        return self._dev
+
+    # ------------------------------------------------------------------ inference
+    def predict_device(self, x):
+        """x: CUDA float32 [N, Hi, Wi, C] (already zero-padded) -> CUDA float32 [N, Hi-10, Wi-10, 32]."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] == self.channels
+        x = x.contiguous()
+        n, h, w = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+        if h < 2 * self.n_layers + 1 or w < 2 * self.n_layers + 1:
+            raise AssertionError("input of %d x %d pixels is too small for five valid 3x3 convolutions" % (h, w))
+        cin = self.channels
+        for l, (k, scale, shift) in enumerate(self._device_weights()):
+            y = torch.empty((n, h - 2, w - 2, self.filters), dtype=torch.float32, device=x.device)
+            _lib.call("rn_conv3x3_bn_relu", x.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
+                      n, h, w, cin, 1 if l < self.n_layers - 1 else 0, current_stream_ptr())
+            self.launches += 1
+            x, h, w, cin = y, h - 2, w - 2, self.filters
+        return x
+
+    def predict(self, X, batch_size=None):
+        """Keras-style: numpy [N, Hi, Wi, C] -> numpy [N, Hi-10, Wi-10, 32]."""
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        return self.predict_device(torch.from_numpy(X).to(device())).cpu().numpy()
+
+    def predict_features(self, scene, view_indices, padding=11):
+        """RayNetForwardPass hook: feature maps of the given views as ONE CUDA tensor
+        [n, H+padding+1, W+padding+1, 32] (zero-padding as forward_pass.py:181-198)."""
+        images = [scene.get_image(v).image for v in view_indices]
+        H, W, C = images[0].shape
+        X = torch.zeros((len(images), H + 2 * padding, W + 2 * padding, C), dtype=torch.float32).pin_memory()
+        for k, im in enumerate(images):
+            X[k, padding:padding + H, padding:padding + W, :] = torch.from_numpy(np.ascontiguousarray(im, dtype=np.float32))
+        self.last_h2d_bytes = X.numel() * 4
+        return self.predict_device(X.to(device(), non_blocking=True))
+
+
+def create_simple_cnn(input_shape=(None, None, 3), seed=0):
+    """models.py:90 signature (input_shape = (H, W, C), sizes may be None)."""
+    return SimpleCNN.random_init(channels=int(input_shape[-1]), seed=seed, trained_like=False)

@@ -1,0 +1,57 @@
+"""the MV-CNN feature extractor (rn_conv3x3_bn_relu / raynet_b200.models.SimpleCNN)
+against the CPU restatement of the reference's Keras model (oracle/cnn_np.py, models.py:90-111)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.mark.parametrize("channels,shape", [(3, (2, 37, 45)), (1, (1, 30, 75)), (3, (3, 11, 11)), (3, (1, 64, 97))])
+def test_simple_cnn_vs_oracle(torch_cuda, channels, shape):
+    from oracle import cnn_np
+    from raynet_b200.models import SimpleCNN
+    rng = np.random.default_rng(3)
+    model = SimpleCNN.random_init(channels=channels, seed=5)
+    X = rng.uniform(0, 1, size=shape + (channels,)).astype(np.float32)
+    got = model.predict(X)
+    ref = cnn_np.simple_cnn_forward(X, model.get_weights())
+    assert got.shape == ref.shape == (shape[0], shape[1] - 10, shape[2] - 10, 32)
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref).max()
+    print("cnn %s: max |features - oracle| = %.2e (max |feature| %.2f)" % (shape, err, scale))
+    assert err <= 1e-5 * max(scale, 1.0)
+    assert model.launches == 5
+
+
+def test_single_layer_entry_point_and_errors(torch_cuda):
+    torch = torch_cuda
+    from oracle import cnn_np
+    from raynet_b200 import _lib
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(1, 20, 41, 32)).astype(np.float32)
+    k = (rng.normal(size=(3, 3, 32, 32)) * 0.1).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, 32).astype(np.float32)
+    shift = rng.normal(size=32).astype(np.float32)
+    d = [torch.from_numpy(a).cuda() for a in (x, k, scale, shift)]
+    out = torch.empty((1, 18, 39, 32), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("rn_conv3x3_bn_relu", d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), out.data_ptr(),
+              1, 20, 41, 32, 0, st)
+    ref = cnn_np.conv3x3_valid(x, k, np.zeros(32)) * scale + shift
+    assert np.abs(out.cpu().numpy() - ref).max() <= 2e-5
+    _lib.call("rn_conv3x3_bn_relu", d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), out.data_ptr(),
+              1, 20, 41, 32, 1, st)
+    assert np.abs(out.cpu().numpy() - np.maximum(ref, 0)).max() <= 2e-5
+    with pytest.raises(NotImplementedError):
+        _lib.call("rn_conv3x3_bn_relu", d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), out.data_ptr(),
+                  1, 20, 41, 7, 0, st)
+    with pytest.raises(AssertionError):
+        _lib.call("rn_conv3x3_bn_relu", d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), out.data_ptr(),
+                  1, 2, 41, 32, 0, st)

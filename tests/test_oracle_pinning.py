@@ -251,3 +251,21 @@ def test_reference_cuda_kernels_compile_for_sm100a():
     out = subprocess.run(["cuobjdump", "-elf", os.path.join(build_ref_cuda.OUT, "raynet_fp_c1.cubin")],
                          capture_output=True, text=True).stdout
     assert ".text.batch_raynet_fp" in out and ".text.batch_complete_depth_estimation" in out
+
+
+def test_cnn_oracle_convolution_semantics():
+    """oracle/cnn_np.py against an explicit loop: 'valid' cross-correlation, channels-last,
+    Keras kernel layout [kh][kw][cin][cout] (models.py:90-111)."""
+    from oracle import cnn_np
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(2, 6, 7, 3))
+    k = rng.normal(size=(3, 3, 3, 4))
+    b = rng.normal(size=4)
+    ref = np.zeros((2, 4, 5, 4))
+    for n in range(2):
+        for y in range(4):
+            for xx in range(5):
+                for o in range(4):
+                    ref[n, y, xx, o] = b[o] + sum(x[n, y + dy, xx + dx, c] * k[dy, dx, c, o]
+                                                  for dy in range(3) for dx in range(3) for c in range(3))
+    assert np.abs(cnn_np.conv3x3_valid(x, k, b) - ref).max() < 1e-12

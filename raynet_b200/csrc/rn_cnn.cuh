@@ -14,7 +14,8 @@
 // output tile for all 32 output channels: the (10 x 34 x CIN) input tile and the 3x3xCINx32 weights
 // sit in shared memory, a thread accumulates 8 pixels x 8 output channels in registers (64 FMAs for
 // every 10 + 6 shared-memory loads of a (ky, cin) step, so the FMA pipe, not the LSU, is the limiter),
-// pixels are padded to CIN + 1 words so that the 8 pixel addresses of a warp fall into 8 banks.
+// the shared-memory layout (channel swizzle for CIN = 32, odd pixel stride otherwise) sends the 8 pixel
+// addresses of a warp to 8 banks; the input tile of the 32-channel layers arrives by 16-byte cp.async.
 // CTAs are persistent (grid = 2 per SM) and keep the weights resident while they walk the tiles.
 #pragma once
 
@@ -23,6 +24,27 @@
 #define RN_CNN_COUT 32
 #define RN_CNN_TH 8
 #define RN_CNN_TW 32
+
+__device__ __forceinline__ uint64_t rn_cnn_pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void rn_cnn_unpack2(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t rn_cnn_fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// channel swizzle of pixel (py, px) of the shared input tile: a multiple of 4 (16-byte groups intact),
+// different for the 8 pixels (4 column blocks x 2 rows) one warp reads in one instruction
+__device__ __forceinline__ int rn_cnn_swz(int py, int px) { return (((px >> 3) & 3) << 3) | ((py & 1) << 2); }
+__device__ __forceinline__ void rn_cnn_cp_async16(float *dst_smem, const float *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
 
 struct ConvArgs {
     const float *in;       // [N][Hi][Wi][CIN]
@@ -35,13 +57,17 @@ struct ConvArgs {
 
 template <int CIN>
 __host__ __device__ constexpr int rn_cnn_smem_words() {
-    return 9 * CIN * RN_CNN_COUT + (RN_CNN_TH + 2) * (RN_CNN_TW + 2) * ((CIN % 2 == 0) ? CIN + 1 : CIN) + 2 * RN_CNN_COUT + 4;
+    return 9 * CIN * RN_CNN_COUT + (RN_CNN_TH + 2) * (RN_CNN_TW + 2) * ((CIN == 32) ? 32 : ((CIN % 2 == 0) ? CIN + 1 : CIN)) + 2 * RN_CNN_COUT + 4;
 }
 
 template <int CIN>
 __global__ void __launch_bounds__(128) conv3x3_kernel(ConvArgs a) {
     extern __shared__ __align__(16) float cnn_smem[];
-    constexpr int PS = (CIN % 2 == 0) ? CIN + 1 : CIN;   // odd pixel stride: the 8 pixel addresses of a warp hit 8 banks
+    // CIN = 32: pixels are 32 words apart and the channel index is XOR-swizzled with the pixel position
+    // (rn_cnn_swz) -- 16-byte groups stay contiguous for cp.async and the 8 pixel addresses of a warp
+    // still hit 8 banks; other CIN: an odd pixel stride does the same job
+    constexpr bool kSwz = (CIN == 32);
+    constexpr int PS = kSwz ? 32 : ((CIN % 2 == 0) ? CIN + 1 : CIN);
     constexpr int TWI = RN_CNN_TW + 2, THI = RN_CNN_TH + 2;
     float *sW = cnn_smem;                             // [9][CIN][32]
     float *sIn = sW + 9 * CIN * RN_CNN_COUT;          // [THI][TWI][PS]
@@ -65,40 +91,62 @@ __global__ void __launch_bounds__(128) conv3x3_kernel(ConvArgs a) {
         __syncthreads();   // the previous tile's reads of sIn are done (and the weights are in place)
         // ---- input tile: rows y0 .. y0+9, columns x0 .. x0+33, zero outside the image ---------------
         const float *src = a.in + (int64_t)img * a.hi * a.wi * CIN;
-        for (int i = tid; i < THI * TWI * CIN; i += 128) {
-            const int c = i % CIN, px = (i / CIN) % TWI, py = i / (CIN * TWI);
-            const int gy = y0 + py, gx = x0 + px;
-            float v = 0.f;
-            if (gy < a.hi && gx < a.wi) v = __ldg(src + ((int64_t)gy * a.wi + gx) * CIN + c);
-            sIn[(py * TWI + px) * PS + c] = v;
+        if constexpr (kSwz) {
+            for (int i = tid; i < THI * TWI * (CIN / 4); i += 128) {      // one 16-byte group of channels per copy
+                const int g4 = i % (CIN / 4), px = (i / (CIN / 4)) % TWI, py = i / ((CIN / 4) * TWI);
+                const int gy = y0 + py, gx = x0 + px;
+                float *dst = sIn + (py * TWI + px) * PS + ((4 * g4) ^ rn_cnn_swz(py, px));
+                if (gy < a.hi && gx < a.wi) rn_cnn_cp_async16(dst, src + ((int64_t)gy * a.wi + gx) * CIN + 4 * g4);
+                else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        } else {
+            for (int i = tid; i < THI * TWI * CIN; i += 128) {
+                const int c = i % CIN, px = (i / CIN) % TWI, py = i / (CIN * TWI);
+                const int gy = y0 + py, gx = x0 + px;
+                float v = 0.f;
+                if (gy < a.hi && gx < a.wi) v = __ldg(src + ((int64_t)gy * a.wi + gx) * CIN + c);
+                sIn[(py * TWI + px) * PS + c] = v;
+            }
         }
         __syncthreads();
         // ---- 8 pixels x 8 channels per thread ----------------------------------------------------------
+        // accumulators as packed pairs of output channels: one FFMA2 (fma.rn.f32x2) performs the two
+        // FMAs of (pixel i, channels 2 qq and 2 qq + 1) -- half the issue slots of scalar FFMAs
+        uint64_t acc2[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc2[i][q] = 0ull;
+#pragma unroll 1
+        for (int ky = 0; ky < 3; ky++) {
+            const float *row = sIn + ((pr + ky) * TWI + pc * 8) * PS;
+            const int sw_lo = kSwz ? rn_cnn_swz(pr + ky, pc * 8) : 0, sw_hi = kSwz ? rn_cnn_swz(pr + ky, pc * 8 + 8) : 0;
+#pragma unroll 2
+            for (int c = 0; c < CIN; c++) {
+                uint64_t v2[10];
+#pragma unroll
+                for (int i = 0; i < 10; i++) {
+                    const float v = row[i * PS + (c ^ (i < 8 ? sw_lo : sw_hi))];
+                    v2[i] = rn_cnn_pack2(v, v);
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                    const ulonglong2 wa = *reinterpret_cast<const ulonglong2 *>(sW + ((ky * 3 + kx) * CIN + c) * RN_CNN_COUT + qg * 8);
+                    const ulonglong2 wb = *reinterpret_cast<const ulonglong2 *>(sW + ((ky * 3 + kx) * CIN + c) * RN_CNN_COUT + qg * 8 + 4);
+                    const uint64_t w2[4] = {wa.x, wa.y, wb.x, wb.y};
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) acc2[i][q] = rn_cnn_fma2(v2[i + kx], w2[q], acc2[i][q]);
+                }
+            }
+        }
         float acc[8][8];
 #pragma unroll
         for (int i = 0; i < 8; i++)
 #pragma unroll
-            for (int q = 0; q < 8; q++) acc[i][q] = 0.f;
-#pragma unroll 1
-        for (int ky = 0; ky < 3; ky++) {
-            const float *row = sIn + ((pr + ky) * TWI + pc * 8) * PS;
-#pragma unroll 2
-            for (int c = 0; c < CIN; c++) {
-                float v[10];
-#pragma unroll
-                for (int i = 0; i < 10; i++) v[i] = row[i * PS + c];
-#pragma unroll
-                for (int kx = 0; kx < 3; kx++) {
-                    const float4 w0 = *reinterpret_cast<const float4 *>(sW + ((ky * 3 + kx) * CIN + c) * RN_CNN_COUT + qg * 8);
-                    const float4 w1 = *reinterpret_cast<const float4 *>(sW + ((ky * 3 + kx) * CIN + c) * RN_CNN_COUT + qg * 8 + 4);
-                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-#pragma unroll
-                        for (int q = 0; q < 8; q++) acc[i][q] = fmaf(v[i + kx], w[q], acc[i][q]);
-                }
-            }
-        }
+            for (int q = 0; q < 4; q++) rn_cnn_unpack2(acc2[i][q], acc[i][2 * q], acc[i][2 * q + 1]);
         // ---- epilogue: folded batch norm (+ ReLU), channels-last store --------------------------------
         const int oy = y0 + pr;
         if (oy < ho) {

@@ -338,7 +338,11 @@ class RayNetForwardPass(ForwardPass):
             self.engine.score_image(k, self._feat_dev, P_dev, view_ids=view_ids, n_feature_slots=len(views))
         # ---- BP sweeps + depth -----------------------------------------------------------------
         self.engine.run_bp(self.bp_iterations)
-        depth = self.engine.depth().cpu().numpy()
+        depth_dev = self.engine.depth()
+        depth_host = self._pinned("depth", (int(depth_dev.shape[0]),), torch.float32)
+        depth_host.copy_(depth_dev, non_blocking=True)       # pinned destination: one DMA, no staging copy
+        torch.cuda.current_stream(dev).synchronize()
+        depth = depth_host.numpy().copy()
         self.d2h_bytes += depth.nbytes
         for k, ref_idx in enumerate(img_ids):
             start, n, _ = self.engine.segments[k]

@@ -55,3 +55,38 @@ def test_single_layer_entry_point_and_errors(torch_cuda):
     with pytest.raises(AssertionError):
         _lib.call("rn_conv3x3_bn_relu", d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), out.data_ptr(),
                   1, 2, 41, 32, 0, st)
+
+
+def test_raynet_forward_pass_from_images(torch_cuda, oracle):
+    """images -> SimpleCNN -> resident ray-potential pipeline -> depth maps, through the reference's
+    generator API; the CNN's two calling conventions (Keras-style predict on host stacks, and the
+    predict_features hook that keeps the feature volume on the device) must give the same depth maps,
+    and the device features must equal the oracle CNN's."""
+    from oracle import cnn_np
+    from raynet_b200.common.generation_parameters import GenerationParameters
+    from raynet_b200.forward_pass import get_forward_pass_factory
+    from raynet_b200.models import SimpleCNN
+    from raynet_b200.synth import SyntheticScene
+    V, H, W, G, D, M = 3, 24, 20, 24, 8, 72
+    scene = SyntheticScene(V, H, W, (G, G, G), with_images=True)
+    gp = GenerationParameters(depth_planes=D, neighbors=V - 1, grid_shape=np.array([G, G, G], np.int32),
+                              max_number_of_marched_voxels=M, padding=11, gamma_mrf=0.05)
+    cnn = SimpleCNN.random_init(channels=3, seed=1)
+
+    class KerasLike(object):        # only the reference's model.predict(X) entry point
+        def predict(self, X):
+            return cnn.predict(X)
+
+    maps = {}
+    for name, model in (("hook", cnn), ("predict", KerasLike())):
+        fp = get_forward_pass_factory("raynet")(model, gp, "sample_in_bbox", scene.image_shape, H * W)
+        maps[name] = list(fp.forward_pass(scene, (0, V, 1)))
+        assert len(maps[name]) == V and all(m.shape == (H, W) and np.isfinite(m).all() for m in maps[name])
+    for a, b in zip(maps["hook"], maps["predict"]):
+        assert np.array_equal(a, b)
+    feats = cnn.predict_features(scene, [0, 1, 2]).cpu().numpy()
+    X = np.zeros((V, H + 22, W + 22, 3), np.float32)
+    for v in range(V):
+        X[v, 11:11 + H, 11:11 + W] = scene.get_image(v).image
+    ref = cnn_np.simple_cnn_forward(X, cnn.get_weights())
+    assert feats.shape == (V, H + 12, W + 12, 32) and np.abs(feats - ref).max() <= 1e-5

@@ -584,3 +584,31 @@ def test_forward_pass_factory_runs(torch_cuda, oracle):
         outs[name] = maps
     with pytest.raises(KeyError):
         get_forward_pass_factory("nope")
+
+
+def test_engine_generic_feature_size(torch_cuda, oracle):
+    """F != 32 takes the generic similarity kernel (one lane per channel): front end of the resident
+    pipeline against the oracle on 16-channel features."""
+    torch = torch_cuda
+    from raynet_b200.engine import RayPotentialEngine
+    from raynet_b200.synth import random_features
+    c = case_c1()
+    F = 16
+    feats_all = random_features(c.V, c.H, c.W, F, 11, seed=9) * np.float32(3.0)
+    feats = np.ascontiguousarray(feats_all[c.view_ids])
+    o = oracle.frontend(c.ray_idxs, feats, c.P, c.P_inv, c.centre, c.vgrid, c.bbox, c.grid, c.M, c.D, c.V, F, c.H,
+                        c.W, 11)
+    eng = RayPotentialEngine(c.M, c.D, c.V, F, c.H, c.W, 11, c.bbox, c.grid, max_rays=c.N, use_distributed=False)
+    eng.set_voxel_grid(c.vgrid)
+    eng.add_image(_d(torch, c.ray_idxs), _d(torch, feats_all), _d(torch, c.P), _d(torch, c.P_inv), _d(torch, c.centre),
+                  view_ids=_d(torch, c.view_ids))
+    eng.finalize_frontend()
+    assert np.array_equal(eng.count.cpu().numpy(), o["cnt"])
+    assert np.array_equal(eng.voxel_indices().cpu().numpy(), o["idx"])
+    s_hat = eng.s_hat[:c.N, :c.M].cpu().numpy()
+    for q in range(c.N):
+        L = int(o["cnt"][q])
+        if L > 0:
+            ref = np.clip(o["S_vox"][q, :L], 1e-5, 1 - 1e-5)
+            ref = ref / ref.sum(dtype=np.float32)
+            assert np.abs(s_hat[q, :L] - ref).max() <= TOL_P

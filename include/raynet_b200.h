@@ -213,6 +213,19 @@ int rn_conv3x3_bn_relu(const float *in, const float *weights, const float *scale
                        int32_t n_images, int32_t height, int32_t width, int32_t channels_in, int32_t relu,
                        void *stream);
 
+/* SURVEY.md 8(f) row 2 -- depth maps -> point cloud with the multi-view consistency check
+ * (pointcloud.py:76-245, PointcloudFromDepthMaps[WithConsistency]).  Per pixel (v, u) of image i:
+ * point = centre_i + depth_i[v][u] * unit ray through (u, v)  ->  points [n][H][W][3];
+ * tau [n][H][W] = max over the image's n_neighbors cameras j of |depth_j[round(proj_j(point))] -
+ * |point - centre_j||, +inf when a projection leaves image j, when the pixel lies within `borders`
+ * of the image edge or when gt (may be NULL) is 0 there.  The caller keeps the points with
+ * tau < consistency_threshold (row-major order = the reference's).  neighbors: int32
+ * [n][n_neighbors] (NULL: no consistency check, tau = 0 for kept pixels).  P [n][3][4],
+ * P_pinv [n][4][3], centre [n][4] are float64 like the reference's camera matrices. */
+int rn_fuse_depth_maps(const float *depth, const float *gt, const double *P, const double *P_pinv, const double *centre,
+                       const int32_t *neighbors, int32_t n_images, int32_t height, int32_t width, int32_t n_neighbors,
+                       int32_t borders, float *points, float *tau, void *stream);
+
 /* The two halves of rn_engine_frontend as separate calls, so that a caller can trace the rays of
  * every reference image (no feature maps needed: sample_in_bbox + DDA -> starts, ends, ray_hdr,
  * codes, count) and bin them while the feature maps are still on their way to the device, and run

@@ -10,6 +10,7 @@
 #include "rn_bp4.cuh"
 #include "rn_simmap3.cuh"
 #include "rn_cnn.cuh"
+#include "rn_fusion.cuh"
 
 namespace {
 
@@ -492,6 +493,19 @@ int rn_conv3x3_bn_relu(const float *in, const float *weights, const float *scale
         case 32: return launch_conv3x3<32>(a, S(stream));
     }
     return fail(RN_ERR_UNSUPPORTED, "conv3x3: %d input channels (supported: 1, 3, 32)", channels_in);
+}
+
+int rn_fuse_depth_maps(const float *depth, const float *gt, const double *P, const double *P_pinv, const double *centre,
+                       const int32_t *neighbors, int32_t n_images, int32_t height, int32_t width, int32_t n_neighbors,
+                       int32_t borders, float *points, float *tau, void *stream) {
+    if (n_images <= 0 || height <= 0 || width <= 0) return RN_OK;
+    if (!depth || !P || !P_pinv || !centre || !points || !tau) return fail(RN_ERR_SHAPE, "rn_fuse_depth_maps: NULL buffer");
+    if (borders < 0 || n_neighbors < 0) return fail(RN_ERR_SHAPE, "rn_fuse_depth_maps: negative borders / n_neighbors");
+    if (neighbors && n_neighbors == 0) neighbors = nullptr;
+    FuseArgs a = {depth, gt, P, P_pinv, centre, neighbors, points, tau, n_images, height, width, n_neighbors, borders};
+    const int64_t total = (int64_t)n_images * height * width;
+    fuse_depth_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(a);
+    return check_launch("fuse_depth_kernel");
 }
 
 int rn_occupancy(const float *acc, float *out, int64_t n, void *stream) {

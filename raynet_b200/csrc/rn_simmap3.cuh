@@ -20,6 +20,9 @@
 
 #include "rn_kernels.cuh"
 
+#ifndef RN_SIMSCORE_MINB
+#define RN_SIMSCORE_MINB 8
+#endif
 #ifndef RN_SM3_RAYS_PER_WARP
 #define RN_SM3_RAYS_PER_WARP 4
 #endif
@@ -63,7 +66,7 @@ __device__ __forceinline__ int rn_feature_offset(const RnDev &p, int base, int f
 // in the projection / gather loops (nothing else competes for registers and shared memory), which
 // is what keeps enough 128-byte feature gathers in flight to load the L2.
 template <int VT>
-__global__ void __launch_bounds__(128) simscore3_kernel(RnDev p, SimMapArgs a) {
+__global__ void __launch_bounds__(128, RN_SIMSCORE_MINB) simscore3_kernel(RnDev p, SimMapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = p.D, V = VT ? VT : p.V;   // VT > 0: compile-time view count, loops fully unrolled

@@ -269,3 +269,19 @@ def test_cnn_oracle_convolution_semantics():
                     ref[n, y, xx, o] = b[o] + sum(x[n, y + dy, xx + dx, c] * k[dy, dx, c, o]
                                                   for dy in range(3) for dx in range(3) for c in range(3))
     assert np.abs(cnn_np.conv3x3_valid(x, k, b) - ref).max() < 1e-12
+
+
+GOLDEN_PC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pointcloud_golden.npz")
+
+
+@pytest.mark.parametrize("borders,thr,nn", [(4, 0.05, 2), (0, 0.02, 3)])
+def test_pointcloud_oracle_vs_reference_execution(borders, thr, nn):
+    """oracle/pointcloud_np.py against the fixture made by executing raynet/pointcloud.py itself."""
+    from oracle import pointcloud_np
+    g = np.load(GOLDEN_PC)
+    key = "b%d_t%g_n%d" % (borders, thr, nn)
+    assert np.array_equal(pointcloud_np.neighbors(g["centre"], nn), g["neigh_" + key])
+    plain = pointcloud_np.fuse(g["depth"], g["gt"], g["P"], g["P_pinv"], g["centre"], borders)
+    assert plain.shape == g["plain_" + key].shape and np.abs(plain - g["plain_" + key]).max() < 1e-12
+    cons = pointcloud_np.fuse(g["depth"], g["gt"], g["P"], g["P_pinv"], g["centre"], borders, thr, nn)
+    assert cons.shape == g["cons_" + key].shape and np.abs(cons - g["cons_" + key]).max() < 1e-12

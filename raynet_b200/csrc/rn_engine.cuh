@@ -159,38 +159,52 @@ __device__ __forceinline__ int rn_dda_codes(const RnDev &p, const float *rs_in, 
     hdr[0] = (uint32_t)cur[0] | ((uint32_t)cur[1] << 16);
     hdr[1] = (uint32_t)cur[2] | ((step[0] < 0 ? 1u : 0u) << 16) | ((step[1] < 0 ? 1u : 0u) << 17) |
              ((step[2] < 0 ? 1u : 0u) << 18);
-    uint32_t lo = 1u, hi = 1u;   // voxel 0: "no step"
-    int ii = 1;
+    // The loop of ray_tracing.pyx:169-197 on counters instead of coordinates: togo_a = steps still to
+    // take along a to stand on the last voxel (all three zero <=> cur == last; an axis that has
+    // overshot goes negative and never returns to zero, like cur != last), rem_a = steps still
+    // possible along a before leaving the grid (negative after the decrement <=> the stepped
+    // coordinate left the grid: stop WITHOUT emitting).  The 32 voxels of one code word are unrolled,
+    // so the bit position is an immediate and the word is stored once.
+    int togo0 = (last[0] - cur[0]) * step[0], togo1 = (last[1] - cur[1]) * step[1], togo2 = (last[2] - cur[2]) * step[2];
+    int rem0 = step[0] > 0 ? g[0] - 1 - cur[0] : cur[0], rem1 = step[1] > 0 ? g[1] - 1 - cur[1] : cur[1],
+        rem2 = step[2] > 0 ? g[2] - 1 - cur[2] : cur[2];
+    float tm0 = tMax[0], tm1 = tMax[1], tm2 = tMax[2];
+    const float td0 = tDelta[0], td1 = tDelta[1], td2 = tDelta[2];
     const int M = p.M;
-    while (!(cur[0] == last[0] && cur[1] == last[1] && cur[2] == last[2]) && ii < M) {
-        bool xy = tMax[0] < tMax[1];
-        float tm = xy ? tMax[0] : tMax[1];
-        int a = xy ? 0 : 1;
-        a = (tm < tMax[2]) ? a : 2;
-        bool ax = (a == 0), ay = (a == 1), az = (a == 2);
-        cur[0] += ax ? step[0] : 0;
-        cur[1] += ay ? step[1] : 0;
-        cur[2] += az ? step[2] : 0;
-        int ca = ax ? cur[0] : (ay ? cur[1] : cur[2]);
-        int ga = ax ? g[0] : (ay ? g[1] : g[2]);
-        if (ca < 0 || ca >= ga) break;
-        tMax[0] = ax ? tMax[0] + tDelta[0] : tMax[0];
-        tMax[1] = ay ? tMax[1] + tDelta[1] : tMax[1];
-        tMax[2] = az ? tMax[2] + tDelta[2] : tMax[2];
-        const int pos = ii & 31;
-        if (pos == 0) { lo = 0u; hi = 0u; }
-        lo |= ((uint32_t)a & 1u) << pos;
-        hi |= ((uint32_t)a >> 1) << pos;
-        if (pos == 31) words[ii >> 5] = make_uint2(lo, hi);
-        ii++;
+    int ii = 1;
+    uint32_t lo = 1u, hi = 1u;   // voxel 0: "no step"
+    bool finished = false;
+    for (int w = 0; !finished; w++) {
+#pragma unroll
+        for (int pos = 0; pos < 32; pos++) {
+            if (pos == 0 && w == 0) continue;
+            if ((togo0 | togo1 | togo2) == 0 || ii >= M) { finished = true; break; }
+            // strict '<': ties X=Y go to the Y/Z branch, any tie with Z goes to Z
+            const bool xy = tm0 < tm1;
+            const float tm = xy ? tm0 : tm1;
+            const bool az = !(tm < tm2);
+            const bool ax = xy && !az, ay = !xy && !az;
+            togo0 -= ax ? 1 : 0; togo1 -= ay ? 1 : 0; togo2 -= az ? 1 : 0;
+            rem0 -= ax ? 1 : 0; rem1 -= ay ? 1 : 0; rem2 -= az ? 1 : 0;
+            if ((rem0 | rem1 | rem2) < 0) { finished = true; break; }
+            tm0 = ax ? tm0 + td0 : tm0;
+            tm1 = ay ? tm1 + td1 : tm1;
+            tm2 = az ? tm2 + td2 : tm2;
+            lo |= ay ? (1u << pos) : 0u;      // code = axis stepped along: x 0, y 1, z 2
+            hi |= az ? (1u << pos) : 0u;
+            ii++;
+        }
+        if (!finished) {
+            words[w] = make_uint2(lo, hi);
+            lo = 0u; hi = 0u;
+        }
     }
-    const int lastpos = (ii - 1) & 31;
-    int w = (ii - 1) >> 5;
-    if (lastpos != 31) {   // flush the partial pair, tail padded with "no step"
-        const uint32_t pad = ~((2u << lastpos) - 1u);
-        words[w] = make_uint2(lo | pad, hi | pad);
+    int nw = (ii + 31) >> 5;
+    if (ii & 31) {   // flush the partial pair, tail padded with "no step"
+        const uint32_t pad = ~((1u << (ii & 31)) - 1u);
+        words[nw - 1] = make_uint2(lo | pad, hi | pad);
     }
-    for (w = w + 1; (w & 3) != 0; w++) words[w] = make_uint2(0xffffffffu, 0xffffffffu);   // pad to a whole chunk
+    for (; (nw & 3) != 0; nw++) words[nw] = make_uint2(0xffffffffu, 0xffffffffu);   // pad to a whole chunk
     return ii;
 }
 

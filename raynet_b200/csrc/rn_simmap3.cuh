@@ -298,12 +298,11 @@ __global__ void __launch_bounds__(128) planemap3_kernel(RnDev p, SimMapArgs a) {
                     const float sum = (__int_as_float(ex.y) - rs[0]) * rayn[0] + (__int_as_float(ey.y) - rs[1]) * rayn[1] +
                                       (__int_as_float(ez.y) - rs[2]) * rayn[2];
                     const float tt = rn_clampf(sum, 1e-4f, 1 - 1e-4f);
-                    // the reference's persistent two-pointer bracket, stateless: the smallest left with
-                    // t <= (left + 1) * step is one of m - 1, m, m + 1 for m = (int)(t (D - 1))
-                    int left = max(0, (int)(tt * fDm1) - 1);
-                    left += (tt > (float)(left + 1) * pstep) ? 1 : 0;
-                    left += (tt > (float)(left + 1) * pstep) ? 1 : 0;
-                    // weights r/(l+r), l/(l+r) with l + r = step:  S[left] + (t - left step) (D - 1) (S[left+1] - S[left])
+                    // the reference's persistent two-pointer bracket (planes_voxels_mapping.cu:54-70) picks the
+                    // planes left, left + 1 around t; the interpolant is continuous and piecewise linear in t, so
+                    // left = floor(t (D - 1)) gives the same value (to rounding) even where the two differ at a
+                    // plane position.  t <= 1 - 1e-4 keeps left <= D - 2.
+                    const int left = min((int)(tt * fDm1), D - 2);
                     const float2 sd = sS2[left];
                     const float out = fmaf((tt - (float)left * pstep) * fDm1, sd.y, sd.x);
                     sVal[i] = out;

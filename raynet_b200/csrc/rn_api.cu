@@ -770,6 +770,11 @@ int rn_engine_depth(const RnParams *p, const int32_t *lin, const int32_t *count,
     a.lin = lin; a.count = count; a.s_hat = s_hat; a.msgs = msgs; a.acc = acc;
     a.axes = axis_centres; a.centres = centres; a.seg_starts = (n_seg > 1) ? seg_starts : nullptr; a.n_seg = n_seg;
     a.depth_map = depth_map; a.S_new = S_new; a.n_rays = n_rays;
+    static const int impl = [] { const char *e = getenv("RN_DEPTH_IMPL"); return e ? atoi(e) : 3; }();
+    if (impl == 3 && !S_new && depth_map && n_rays > 0) {   // resident fast path (rn_bp4.cuh)
+        depth3_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, S(stream)>>>(d, a);
+        return check_launch("depth3_kernel");
+    }
     return launch_depth2<false>(d, a, S(stream));
 }
 

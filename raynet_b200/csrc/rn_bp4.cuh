@@ -201,3 +201,128 @@ __global__ void __launch_bounds__(128) bp4_kernel(RnDev p, Bp2Args a) {
         }
     }
 }
+
+
+// =======================================================================================
+// a8 + a9 on the resident layout: depth re-estimation + arg-max -> depth, warp per ray.
+// depth2_kernel (rn_engine.cuh) serves every layout and the S_new output of the tests and was
+// issue-bound (81 % of the issue slots, 1070 warp instructions per ray); this is its resident-only
+// fast path: masks in the last chunk only, cache policies created once, o / q formed directly
+// from min(o, 1 - o), the reference image of a ray looked up by one lane with a guess-and-check.
+// =======================================================================================
+__device__ __forceinline__ void rn_occ_oq(float acc, float msg, float &o, float &q) {
+    const float x = acc - msg;
+    const float u = fmaxf(rn_rcp(1.0f + rn_ex2(fabsf(x) * 1.4426950408889634f)), 1e-4f);   // min(o, 1 - o), clipped
+    const bool pos = x >= 0.f;
+    o = pos ? 1.0f - u : u;
+    q = pos ? u : 1.0f - u;
+}
+
+template <bool kTail>
+__device__ __forceinline__ void rn_depth3_chunk(const Depth2Args &a, const int32_t *lin_row, const float *s_row,
+                                                const float *m_row, float *sX, int c, int L, int lane, uint64_t pol_stream,
+                                                uint64_t pol_keep, float &carry_cp, float &bestv, int &besti) {
+    float ga[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = c * RN_CHUNK + 32 * j + lane;
+        ga[j] = 0.f;
+        if (!kTail || i < L) ga[j] = rn_ld_acc_pol(a.acc + rn_ld_stream_s32(lin_row + i, pol_stream), pol_keep);
+    }
+    const int i0 = c * RN_CHUNK + 4 * lane;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), m4 = s4;
+    if (!kTail || i0 < L) {
+        s4 = rn_ld_stream4_pol(s_row + i0, pol_stream);
+        m4 = rn_ld_stream4_pol(m_row + i0, pol_stream);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; j++) sX[32 * j + lane] = ga[j];
+    __syncwarp();
+    const float4 acc4 = *reinterpret_cast<const float4 *>(sX + 4 * lane);
+    const float accv[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+    float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+    float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+    float o[4], q[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (kTail) {   // slots beyond the ray: s = 0 -> a_i = 0, never the maximum of a ray with L > 1
+            const bool ok = i0 + j < L;
+            sv[j] = ok ? sv[j] : 0.f;
+            mv[j] = ok ? mv[j] : 0.f;
+        }
+        rn_occ_oq(accv[j], mv[j], o[j], q[j]);
+    }
+    const float lp0 = q[0], lp1 = lp0 * q[1], lp2 = lp1 * q[2], lp3 = lp2 * q[3];
+    const float inc = rn_warp_incl_scan_mul(lp3, lane);
+    float exc = __shfl_up_sync(RN_FULL_MASK, inc, 1);
+    if (lane == 0) exc = 1.f;
+    const float base = carry_cp * exc;
+    carry_cp = carry_cp * __shfl_sync(RN_FULL_MASK, inc, 31);
+    const float av[4] = {o[0] * (base * sv[0]), o[1] * ((base * lp0) * sv[1]), o[2] * ((base * lp1) * sv[2]),
+                         o[3] * ((base * lp2) * sv[3])};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool better = kTail ? (i0 + j < L && av[j] > bestv) : (av[j] > bestv);
+        bestv = better ? av[j] : bestv;
+        besti = better ? i0 + j : besti;
+    }
+}
+
+__global__ void __launch_bounds__(128) depth3_kernel(RnDev p, Depth2Args a) {
+    __shared__ __align__(16) float sXall[4][128];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * 4 + wid;
+    if (r >= a.n_rays) return;
+    float *sX = sXall[wid];
+    const int L = __ldg(a.count + r);
+    const uint64_t pol_stream = rn_policy_evict_first();
+    const uint64_t pol_keep = rn_policy_evict_last();
+    const int32_t *lin_row = a.lin + r * (int64_t)p.row_stride;
+    const float *s_row = a.s_hat + r * (int64_t)p.row_stride;
+    const float *m_row = a.msgs + r * (int64_t)p.row_stride;
+    float bestv = -INFINITY;
+    int besti = 0;
+    if (L > 1) {   // mrf_np.py:376-377: rays with count <= 1 keep an all-zero row
+        const int nch = (L + RN_CHUNK - 1) / RN_CHUNK;
+        float carry_cp = 1.f;
+        for (int c = 0; c < nch - 1; c++)
+            rn_depth3_chunk<false>(a, lin_row, s_row, m_row, sX, c, L, lane, pol_stream, pol_keep, carry_cp, bestv, besti);
+        rn_depth3_chunk<true>(a, lin_row, s_row, m_row, sX, nch - 1, L, lane, pol_stream, pol_keep, carry_cp, bestv, besti);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {   // first maximum over the ray (raynet_fp.py:193-205)
+            const float ov = __shfl_xor_sync(RN_FULL_MASK, bestv, d);
+            const int oi = __shfl_xor_sync(RN_FULL_MASK, besti, d);
+            if (ov > bestv || (ov == bestv && oi < besti)) { bestv = ov; besti = oi; }
+        }
+    }
+    if (lane == 0) {
+        // voxel of the arg-max slot; an all-zero row selects slot 0 (the first voxel of the ray or, for an
+        // empty ray, the zero-filled triplet (0, 0, 0); raynet_fp.py:206-226)
+        int x = 0, y = 0, z = 0;
+        if (L >= 1) rn_unbrick(p, __ldg(lin_row + ((L > 1) ? besti : 0)), x, y, z);
+        int seg = 0;
+        if (a.seg_starts) {
+            // usual case: every image has the same number of rays -> the image is r / rays-per-image;
+            // checked against the table, binary search otherwise
+            const int64_t len = __ldg(a.seg_starts + 1);
+            const int guess = len > 0 ? (int)min((int64_t)(a.n_seg - 1), r / len) : 0;
+            if (__ldg(a.seg_starts + guess) <= r && r < __ldg(a.seg_starts + guess + 1)) {
+                seg = guess;
+            } else {
+                int lo_s = 0, hi_s = a.n_seg;
+                while (hi_s - lo_s > 1) {
+                    const int mid = (lo_s + hi_s) >> 1;
+                    if (__ldg(a.seg_starts + mid) <= r) lo_s = mid; else hi_s = mid;
+                }
+                seg = lo_s;
+            }
+        }
+        const float *C = a.centres + 4 * seg;
+        const float cc[3] = {__ldg(a.axes + x), __ldg(a.axes + p.gx + y), __ldg(a.axes + p.gx + p.gy + z)};
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { const float dd = cc[i] - __ldg(C + i); sum += dd * dd; }
+        a.depth_map[r] = sqrtf(sum);
+    }
+}

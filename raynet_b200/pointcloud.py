@@ -61,10 +61,13 @@ class PointcloudFromDepthMaps(Pointcloud):
             P = np.stack([np.asarray(c.P, np.float64) for c in cams])
             P_pinv = np.stack([np.asarray(c.P_pinv, np.float64) for c in cams])
             centre = np.stack([np.asarray(c.center, np.float64).ravel()[:4] for c in cams])
-            gt = None
+            gt = None       # ground-truth mask (pointcloud.py:118-121); a scene without ground truth keeps every pixel
             if hasattr(self._scene, "get_depth_map"):
-                gt = np.stack([np.asarray(self._scene.get_depth_map(i), np.float32) for i in self._frame_idxs])
-                assert gt.shape == depth.shape
+                try:
+                    gt = np.stack([np.asarray(self._scene.get_depth_map(i), np.float32) for i in self._frame_idxs])
+                    assert gt.shape == depth.shape
+                except NotImplementedError:
+                    gt = None
             nb = self._neighbors()
             t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
             d_depth, d_gt, d_P, d_Pi, d_C, d_nb = t(depth), t(gt), t(P), t(P_pinv), t(centre), t(nb)

@@ -153,3 +153,68 @@ def test_two_rank_gloo_sharded_bp_matches_single_process(tmp_path, oracle):
     line = [l for l in outs[0].splitlines() if l.startswith("RESULT")][0]
     err, merr = (float(x) for x in line.split()[1:])
     assert err <= 1e-5 and merr <= 1e-3
+
+
+# ----------------------------------------------------------------------------- on-disk scenes
+GOLDEN_SCENE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scene_golden.npz")
+
+
+def test_adjacent_frames_match_reference_execution():
+    """get_adjacent_frames_idxs against 500+ outputs of the reference's own function
+    (tests/golden/make_scene_golden.py) and the four cases of the reference's tests/test_scene.py:110-120."""
+    from raynet_b200.common.scene import get_adjacent_frames_idxs
+    g = np.load(GOLDEN_SCENE)
+    for (ref, n_frames, n_adj, skip), want in zip(g["cases"], g["neighbors"]):
+        got = get_adjacent_frames_idxs(int(ref), int(n_frames), int(n_adj), int(skip))
+        assert np.array_equal(got, want[:n_adj]), (ref, n_frames, n_adj, skip, got, want)
+    assert np.array_equal(get_adjacent_frames_idxs(0, 50, 4, 0), [1, 2, 3, 4])
+    assert np.array_equal(get_adjacent_frames_idxs(1, 50, 4, 0), [0, 2, 3, 4])
+    assert np.array_equal(get_adjacent_frames_idxs(35, 50, 4, 0), [33, 34, 36, 37])
+    assert np.array_equal(get_adjacent_frames_idxs(50, 50, 4, 0), [46, 47, 48, 49])
+    with pytest.raises(ValueError):
+        get_adjacent_frames_idxs(51, 50, 4, 0)
+
+
+def test_restrepo_scene_on_disk(tmp_path):
+    """A scene written in the Restrepo layout reads back: sorted files, K / R / t, bounding box, image
+    scaling, neighbours, voxel grid; and, when the reference tree is present, its mock dataset parses to
+    the values the reference's own parser produced (tests/golden/scene_golden.npz)."""
+    from PIL import Image as PILImage
+    from raynet_b200.common.scene import RestrepoScene, parse_scene_info
+    from raynet_b200.synth import ring_cameras
+    H, W, n = 12, 16, 6
+    os.makedirs(tmp_path / "imgs")
+    os.makedirs(tmp_path / "cams_krt")
+    cams = ring_cameras(n, H, W)
+    rng = np.random.RandomState(0)
+    pix = rng.randint(0, 256, size=(n, H, W, 3)).astype(np.uint8)
+    for k, c in enumerate(cams):
+        PILImage.fromarray(pix[k]).save(str(tmp_path / "imgs" / ("frame%05d.png" % k)))
+        with open(str(tmp_path / "cams_krt" / ("frame%05d_cam.txt" % k)), "w") as f:
+            for M in (c.K, c.R):
+                f.write("\n".join(" ".join("%.9g" % v for v in row) for row in M) + "\n\n")
+            f.write(" ".join("%.9g" % v for v in c.t.ravel()) + "\n")
+    with open(str(tmp_path / "scene_info.xml"), "w") as f:
+        f.write('<bwm_info_for_boxm2><bbox maxx="1.0" maxy="1" maxz="1.5" minx="-1" miny="-1.0 " minz="-0.5"></bbox>'
+                '<resolution val="0.01"></resolution></bwm_info_for_boxm2>')
+    s = RestrepoScene(str(tmp_path))
+    assert s.n_images == n and s.image_shape == (H, W)
+    assert np.array_equal(s.bbox, np.array([[-1, -1, -0.5, 1, 1, 1.5]], np.float32))
+    im = s.get_image(2)
+    assert im.image.dtype == np.float32 and np.array_equal(im.image, pix[2].astype(np.float32) / np.float32(255.))
+    assert np.allclose(im.camera.K, cams[2].K, rtol=1e-6) and np.allclose(im.camera.t, cams[2].t, rtol=1e-6, atol=1e-7)
+    assert [int(j) for j in s._get_neighbor_idxs(0, 4)] == [1, 2, 3, 4]
+    assert len(s.get_image_with_neighbors(3)) == 5 and s.get_image_with_neighbors(3)[0] is s.get_image(3)
+    assert s.voxel_grid(np.array([4, 4, 4])).shape == (3, 4, 4, 4)
+    sd = RestrepoScene(str(tmp_path), select_neighbors_based_on="distance")
+    assert len(set(int(j) for j in sd._get_neighbor_idxs(0, 3)) - {0}) == 3
+    ref_scene = "/root/reference/tests/restrepo_mock_dataset/scene_1"
+    if os.path.isdir(ref_scene):
+        g = np.load(GOLDEN_SCENE)
+        r = RestrepoScene(ref_scene)
+        assert np.array_equal(parse_scene_info(os.path.join(ref_scene, "scene_info.xml")), g["bbox"])
+        assert r.n_images == g["K"].shape[0] and r.image_shape == (720, 1280)
+        for i in range(r.n_images):
+            c = r.get_image(i).camera
+            assert np.array_equal(c.K, g["K"][i]) and np.array_equal(c.R, g["R"][i]) and np.array_equal(c.t, g["t"][i])
+            assert np.array_equal(c.P, g["P"][i]) and np.array_equal(c.center, g["center"][i])

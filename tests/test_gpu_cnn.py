@@ -90,3 +90,41 @@ def test_raynet_forward_pass_from_images(torch_cuda, oracle):
         X[v, 11:11 + H, 11:11 + W] = scene.get_image(v).image
     ref = cnn_np.simple_cnn_forward(X, cnn.get_weights())
     assert feats.shape == (V, H + 12, W + 12, 32) and np.abs(feats - ref).max() <= 1e-5
+
+
+def test_dataset_on_disk_to_point_cloud(torch_cuda, tmp_path):
+    """SURVEY.md 8(f) rows 4 + 1 + path + 2 in one go: a scene in the Restrepo layout on disk ->
+    RestrepoScene -> SimpleCNN features -> ray-potential inference -> depth maps -> fused point cloud."""
+    import os
+    from PIL import Image as PILImage
+    from raynet_b200.common.generation_parameters import GenerationParameters
+    from raynet_b200.common.scene import RestrepoScene
+    from raynet_b200.forward_pass import get_forward_pass_factory
+    from raynet_b200.models import SimpleCNN
+    from raynet_b200.pointcloud import get_pointcloud
+    from raynet_b200.synth import ring_cameras
+    H, W, n, G, D, M = 24, 32, 6, 24, 8, 72
+    os.makedirs(tmp_path / "imgs")
+    os.makedirs(tmp_path / "cams_krt")
+    rng = np.random.RandomState(1)
+    for k, c in enumerate(ring_cameras(n, H, W)):
+        PILImage.fromarray(rng.randint(0, 256, size=(H, W, 3)).astype(np.uint8)).save(str(tmp_path / "imgs" / ("f%03d.png" % k)))
+        with open(str(tmp_path / "cams_krt" / ("f%03d_cam.txt" % k)), "w") as f:
+            for Mx in (c.K, c.R):
+                f.write("\n".join(" ".join("%.9g" % v for v in row) for row in Mx) + "\n\n")
+            f.write(" ".join("%.9g" % v for v in c.t.ravel()) + "\n")
+    with open(str(tmp_path / "scene_info.xml"), "w") as f:
+        f.write('<bwm_info_for_boxm2><bbox maxx="1" maxy="1" maxz="1" minx="-1" miny="-1" minz="-1"></bbox></bwm_info_for_boxm2>')
+    scene = RestrepoScene(str(tmp_path))
+    gp = GenerationParameters(depth_planes=D, neighbors=4, grid_shape=np.array([G, G, G], np.int32),
+                              max_number_of_marched_voxels=M, padding=11, gamma_mrf=0.05)
+    fp = get_forward_pass_factory("raynet")(SimpleCNN.random_init(3, seed=2), gp, "sample_in_bbox", scene.image_shape, H * W)
+    maps = list(fp.forward_pass(scene, (0, n, 1)))
+    assert len(maps) == n and all(m.shape == (H, W) and np.isfinite(m).all() and (m > 0).all() for m in maps)
+    pc = get_pointcloud(scene, list(range(n)), maps, True, borders=2, consistency_threshold=0.5, n_neighbors=2)
+    pts = pc.points
+    assert pts.shape[0] == 3 and np.isfinite(pts).all()
+    plain = get_pointcloud(scene, list(range(n)), maps, False, borders=2).points
+    assert plain.shape[1] == n * (H - 4) * (W - 4) and pts.shape[1] <= plain.shape[1]
+    # every fused point lies on its pixel's ray at the predicted depth: inside the bounding box (+ one voxel)
+    assert (np.abs(plain) <= 1.0 + 2.0 / G + 1e-4).all()

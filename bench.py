@@ -297,7 +297,7 @@ def run_reference_arm(args, cfg):
     from oracle import oracle as orc
     orc.build()
     cores = orc.num_threads()
-    sample = cpu_calibrated_sample(cfg, 2.0)
+    sample = cpu_calibrated_sample(cfg, 3.0)
     for _ in range(args.warmup):
         sample.step()
     times = [sample.step() for _ in range(args.steps)]

@@ -226,6 +226,15 @@ int rn_fuse_depth_maps(const float *depth, const float *gt, const double *P, con
                        const int32_t *neighbors, int32_t n_images, int32_t height, int32_t width, int32_t n_neighbors,
                        int32_t borders, float *points, float *tau, void *stream);
 
+/* Exact Euclidean nearest-neighbour distance of every query point to a target cloud -- the quantity
+ * behind the reference's accuracy / completeness metrics (metrics.py:156-236, an sklearn KD-tree there).
+ * The caller bins the targets into a uniform grid: sorted_targets float32 [nt][3] ordered by cell id
+ * (x fastest: id = (z * dims[1] + y) * dims[0] + x, cell = floor((p - origin) / cell) clamped),
+ * cell_start int32 [dims[0]*dims[1]*dims[2] + 1].  origin, dims: HOST pointers to 3 values.
+ * max_rings <= 0: search until found.  out float32 [n_query]. */
+int rn_nn_grid_distances(const float *query, int64_t n_query, const float *sorted_targets, const int32_t *cell_start,
+                         const float *origin, float cell, const int32_t *dims, int32_t max_rings, float *out, void *stream);
+
 /* The two halves of rn_engine_frontend as separate calls, so that a caller can trace the rays of
  * every reference image (no feature maps needed: sample_in_bbox + DDA -> starts, ends, ray_hdr,
  * codes, count) and bin them while the feature maps are still on their way to the device, and run

@@ -72,6 +72,7 @@ SIGNATURES = {
     "rn_engine_similarity": [_PP, _PTR, _PTR, _I32] + [_PTR] * 9 + [_I64, _PTR],
     "rn_conv3x3_bn_relu": [_PTR] * 5 + [_I32] * 5 + [_PTR],
     "rn_fuse_depth_maps": [_PTR] * 6 + [_I32] * 5 + [_PTR, _PTR, _PTR],
+    "rn_nn_grid_distances": [_PTR, _I64, _PTR, _PTR, _PTR, ctypes.c_float, _PTR, _I32, _PTR, _PTR],
     "rn_engine_bin_rays": [_PP, _PTR, _I64, _I64, _PTR, _PTR, _PTR],
     "rn_engine_bp_iteration": [_PP] + [_PTR] * 8 + [_I32, _I32, _I64, _PTR],
     "rn_engine_depth": [_PP] + [_PTR] * 8 + [_I32, _PTR, _PTR, _I64, _PTR],

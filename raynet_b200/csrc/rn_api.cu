@@ -508,6 +508,19 @@ int rn_fuse_depth_maps(const float *depth, const float *gt, const double *P, con
     return check_launch("fuse_depth_kernel");
 }
 
+int rn_nn_grid_distances(const float *query, int64_t n_query, const float *sorted_targets, const int32_t *cell_start,
+                         const float *origin, float cell, const int32_t *dims, int32_t max_rings, float *out, void *stream) {
+    if (n_query <= 0) return RN_OK;
+    if (!query || !sorted_targets || !cell_start || !origin || !dims || !out) return fail(RN_ERR_SHAPE, "rn_nn_grid_distances: NULL buffer");
+    if (!(cell > 0.f) || dims[0] < 1 || dims[1] < 1 || dims[2] < 1) return fail(RN_ERR_SHAPE, "rn_nn_grid_distances: bad grid");
+    NnArgs a = {};
+    a.query = query; a.target = sorted_targets; a.cell_start = cell_start; a.out = out; a.nq = n_query; a.cell = cell;
+    for (int i = 0; i < 3; i++) { a.origin[i] = origin[i]; a.dims[i] = dims[i]; }
+    a.max_rings = max_rings > 0 ? max_rings : (1 << 30);
+    nn_grid_kernel<<<(unsigned)((n_query + 127) / 128), 128, 0, S(stream)>>>(a);
+    return check_launch("nn_grid_kernel");
+}
+
 int rn_occupancy(const float *acc, float *out, int64_t n, void *stream) {
     if (n <= 0) return RN_OK;
     occupancy_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(acc, out, n);

@@ -68,3 +68,57 @@ __global__ void __launch_bounds__(256) fuse_depth_kernel(FuseArgs a) {
     }
     a.tau[t] = (float)tau;
 }
+
+// =======================================================================================
+// Nearest-neighbour distances between two point clouds (pointcloud.py:64-73, metrics.py:156-236:
+// accuracy = distance of every predicted point to the ground-truth cloud, completeness the other
+// way round; the reference asks an sklearn KD-tree).  Here the target cloud is binned into a
+// uniform grid on the host side (torch sort by cell + cell_start offsets); one thread per query
+// scans the cells ring by ring (Chebyshev distance r around its own cell) and stops as soon as
+// the best squared distance is within (r h)^2: every unscanned point lies in a cell at Chebyshev
+// distance >= r + 1 and is therefore further than r h away.  Exact, Euclidean, float32.
+// =======================================================================================
+struct NnArgs {
+    const float *query;        // [nq][3]
+    const float *target;       // [nt][3] sorted by cell
+    const int32_t *cell_start; // [nx*ny*nz + 1]
+    float *out;                // [nq] distance to the nearest target point
+    int64_t nq;
+    float origin[3];
+    float cell;                // edge length h
+    int dims[3];
+    int max_rings;
+};
+
+__global__ void __launch_bounds__(128) nn_grid_kernel(NnArgs a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nq) return;
+    const float q[3] = {a.query[3 * t], a.query[3 * t + 1], a.query[3 * t + 2]};
+    int c[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) c[i] = min(max((int)floorf((q[i] - a.origin[i]) / a.cell), 0), a.dims[i] - 1);
+    float best = INFINITY;
+    const int rmax = min(a.max_rings, max(a.dims[0], max(a.dims[1], a.dims[2])));
+    for (int r = 0; r <= rmax; r++) {
+        const int z0 = max(c[2] - r, 0), z1 = min(c[2] + r, a.dims[2] - 1);
+        const int y0 = max(c[1] - r, 0), y1 = min(c[1] + r, a.dims[1] - 1);
+        const int x0 = max(c[0] - r, 0), x1 = min(c[0] + r, a.dims[0] - 1);
+        for (int z = z0; z <= z1; z++) {
+            for (int y = y0; y <= y1; y++) {
+                const bool face = (abs(z - c[2]) == r) || (abs(y - c[1]) == r);   // whole x-run is on the shell
+                for (int x = x0; x <= x1; x += (face ? 1 : max(x1 - x0, 1))) {    // otherwise only its two ends
+                    if (!face && abs(x - c[0]) != r) continue;
+                    const int64_t cellid = ((int64_t)z * a.dims[1] + y) * a.dims[0] + x;
+                    const int s = a.cell_start[cellid], e = a.cell_start[cellid + 1];
+                    for (int k = s; k < e; k++) {
+                        const float dx = a.target[3 * k] - q[0], dy = a.target[3 * k + 1] - q[1], dz = a.target[3 * k + 2] - q[2];
+                        best = fminf(best, dx * dx + dy * dy + dz * dz);
+                    }
+                }
+            }
+        }
+        const float reach = (float)r * a.cell;
+        if (best <= reach * reach) break;
+    }
+    a.out[t] = sqrtf(best);
+}

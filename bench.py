@@ -410,9 +410,13 @@ def run_gpu_arm(args, cfg):
         if record:
             ev[0].record()
         eng.reset()
+        # same order as RayNetForwardPass.forward_pass: trace every image, bin the rays (the class sizes
+        # travel to the host on a side stream meanwhile), then similarity + mapping per image
         for (P, P_inv, centre, vids) in per_image:
-            eng.add_image(ids, feats, P, P_inv, centre, view_ids=vids, n_feature_slots=len(my_views))
+            eng.trace_image(ids, P_inv, centre)
         eng.finalize_frontend()
+        for k, (P, P_inv, centre, vids) in enumerate(per_image):
+            eng.score_image(k, feats, P, view_ids=vids, n_feature_slots=len(my_views))
         if record:
             ev[1].record()
         eng.run_bp(I)

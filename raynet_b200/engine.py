@@ -73,6 +73,10 @@ class RayPotentialEngine(object):
         self.acc_prev = torch.full((self.GB,), self.prior, dtype=torch.float32, **kw)
         self.acc_new = torch.empty((self.GB,), dtype=torch.float32, **kw)
         self.axes = torch.zeros((sum(self.grid_shape),), dtype=torch.float32, **kw)
+        self._side = None                # side stream + pinned buffer for the class-size read-back
+        self._sizes_host = None
+        self._pending_sizes = None
+        self._binned = False
         self.starts = self.ends = None   # float32 [capacity, 3], allocated by the first trace_image()
         self._class_scratch = torch.zeros((2 * self.n_classes,), dtype=torch.int64, **kw)
         self._class_offsets = None  # host int64 [n_classes + 1] (ctypes array) once rays are binned
@@ -111,6 +115,8 @@ class RayPotentialEngine(object):
         self.n_rays = 0
         self.segments = []
         self._class_offsets = None
+        self._binned = False
+        self._pending_sizes = None
         self.class_sizes = None
         self._centres = None
         self._seg_starts = None
@@ -147,6 +153,8 @@ class RayPotentialEngine(object):
         self.segments.append((start, n, centre))
         self.n_rays = start + n
         self._class_offsets = None
+        self._binned = False
+        self._pending_sizes = None
         return len(self.segments) - 1
 
     def score_image(self, k, features, P, view_ids=None, n_feature_slots=None):
@@ -175,7 +183,32 @@ class RayPotentialEngine(object):
         self._centres = cen
         self._seg_starts = torch.tensor([s for (s, _, _) in self.segments] + [self.n_rays], dtype=torch.int64,
                                         device=self.dev)
-        sizes = self._class_scratch[:self.n_classes].cpu().numpy().astype(np.int64)     # the one sync
+        # the one device->host read: on a side stream into pinned memory, so that kernels the caller
+        # queues on its own stream meanwhile (the similarity of forward_pass / bench) are not waited for
+        main = torch.cuda.current_stream(self.dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+            self._sizes_host = torch.empty((self.n_classes,), dtype=torch.int64).pin_memory()
+        binned = torch.cuda.Event()
+        binned.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(binned)
+            self._sizes_host.copy_(self._class_scratch[:self.n_classes], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._pending_sizes = done
+        self._binned = True
+
+    def _resolve_classes(self):
+        """Wait for the class sizes read back by finalize_frontend() (normally long complete: the
+        caller has queued the similarity kernels in the meantime) and turn them into launch offsets."""
+        if not self._binned:
+            self.finalize_frontend()
+        if self._pending_sizes is None:
+            return self.max_count
+        self._pending_sizes.synchronize()
+        self._pending_sizes = None
+        sizes = self._sizes_host.numpy().astype(np.int64)
         self.class_sizes = sizes
         off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         self._class_offsets = (ctypes.c_int64 * (self.n_classes + 1))(*[int(v) for v in off])
@@ -186,7 +219,7 @@ class RayPotentialEngine(object):
     # ------------------------------------------------------------------ BP
     def bp_iteration(self):
         if self._class_offsets is None:
-            self.finalize_frontend()
+            self._resolve_classes()
         st = current_stream_ptr()
         _lib.call("rn_fill_f32", _ptr(self.acc_new), sharding.seed_value(self.rank, self.prior), self.GB, st)
         if self.sweep_events is not None:
@@ -241,7 +274,7 @@ class RayPotentialEngine(object):
     def depth(self, depth_out=None, S_new=None):
         """Depth per ray (flat, ray order of add_image calls), all images in one launch."""
         if self._class_offsets is None:
-            self.finalize_frontend()
+            self._resolve_classes()
         if depth_out is None:
             depth_out = torch.empty((self.n_rays,), dtype=torch.float32, device=self.dev)
         if self.iterations_done == 0:

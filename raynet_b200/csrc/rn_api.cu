@@ -699,7 +699,9 @@ int rn_engine_similarity(const RnParams *p, const float *features, const int32_t
     a.axes = axis_centres; a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.lin = lin;
     a.n_rays = n_rays;
     static const int impl = [] { const char *e = getenv("RN_SIMMAP_IMPL"); return e ? atoi(e) : 3; }();
-    if (impl == 3 && d.F == 32) return launch_simmap3(d, a, S(stream));
+    // simscore3 addresses the feature volume with 32-bit BYTE offsets: below 4 GiB only
+    const int64_t feat_elems = (int64_t)(view_ids ? n_feature_slots : d.V) * d.fh * d.fw * d.F;
+    if (impl == 3 && d.F == 32 && feat_elems < (1ll << 30)) return launch_simmap3(d, a, S(stream));
     return launch_simmap<false>(d, a, true, S(stream));
 }
 

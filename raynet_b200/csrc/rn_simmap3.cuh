@@ -62,6 +62,69 @@ __device__ __forceinline__ int rn_feature_offset(const RnDev &p, int base, int f
     return base + (fy * p.fw + fx) * p.F;
 }
 
+// Step 2 of the similarity: 8 lanes cover one 32-channel vector (LDG.128 each), 4 planes per warp
+// instruction.  sOff holds BYTE offsets (uint32) into the feature volume, so an address is the lane's
+// 64-bit base plus a 32-bit offset: two integer instructions instead of the four of a sign-extended
+// element index.  kRef: the reference view's vector (the same for every plane) was fetched once and
+// seeds the accumulators; separate instantiations keep predicated copies out of the loop.
+template <int VT, bool kRef>
+__device__ __forceinline__ void rn_plane_scores(const RnDev &p, const SimMapArgs &a, const int *sOff, float *sS,
+                                                int ref_off, int lane) {
+    const int D = p.D, V = VT ? VT : p.V, VP = (V + 3) & ~3;
+    const float inv_pairs = 0.5f / (float)p.npairs;
+    const int g = lane >> 3;
+    const char *featb = reinterpret_cast<const char *>(a.features) + (lane & 7) * 16;
+    auto vec = [&](int off) { return __ldg(reinterpret_cast<const float4 *>(featb + (uint32_t)off)); };
+    uint64_t r01 = 0, r23 = 0, rq01 = 0, rq23 = 0;
+    if (kRef) {
+        const float4 f = vec(ref_off);
+        r01 = rn_pack2(f.x, f.y); r23 = rn_pack2(f.z, f.w);
+        rq01 = rn_fma2(r01, r01, 0); rq23 = rn_fma2(r23, r23, 0);
+    }
+    constexpr int V0 = kRef ? 1 : 0;
+#pragma unroll 2
+    for (int k0 = 0; k0 < D; k0 += 4) {
+        const int k = min(k0 + g, D - 1);
+        uint64_t s01 = r01, s23 = r23, q01 = rq01, q23 = rq23;
+        if constexpr (VT > 0) {
+            constexpr int NG = (VT + 3) / 4;
+            const int4 *offk = reinterpret_cast<const int4 *>(sOff + k * VP);
+            int off[NG * 4];
+#pragma unroll
+            for (int gq = 0; gq < NG; gq++) {
+                const int4 o4 = offk[gq];
+                off[4 * gq] = o4.x; off[4 * gq + 1] = o4.y; off[4 * gq + 2] = o4.z; off[4 * gq + 3] = o4.w;
+            }
+            float4 f[VT];
+#pragma unroll
+            for (int v = V0; v < VT; v++) f[v] = vec(off[v]);
+#pragma unroll
+            for (int v = V0; v < VT; v++) {
+                const uint64_t f01 = rn_pack2(f[v].x, f[v].y), f23 = rn_pack2(f[v].z, f[v].w);
+                s01 = rn_add2(s01, f01); s23 = rn_add2(s23, f23);
+                q01 = rn_fma2(f01, f01, q01); q23 = rn_fma2(f23, f23, q23);
+            }
+        } else {
+            const int *offs = sOff + k * VP;
+#pragma unroll 4
+            for (int v = V0; v < V; v++) {
+                const float4 fv = vec(offs[v]);
+                const uint64_t f01 = rn_pack2(fv.x, fv.y), f23 = rn_pack2(fv.z, fv.w);
+                s01 = rn_add2(s01, f01); s23 = rn_add2(s23, f23);
+                q01 = rn_fma2(f01, f01, q01); q23 = rn_fma2(f23, f23, q23);
+            }
+        }
+        float sx, sy, sz, sw, qx, qy, qz, qw;
+        rn_unpack2(s01, sx, sy); rn_unpack2(s23, sz, sw);
+        rn_unpack2(q01, qx, qy); rn_unpack2(q23, qz, qw);
+        float val = fmaf(sx, sx, fmaf(sy, sy, fmaf(sz, sz, fmaf(sw, sw, -((qx + qy) + (qz + qw))))));
+        val += __shfl_xor_sync(RN_FULL_MASK, val, 1);
+        val += __shfl_xor_sync(RN_FULL_MASK, val, 2);
+        val += __shfl_xor_sync(RN_FULL_MASK, val, 4);
+        if ((lane & 7) == 0 && k0 + g < D) sS[k0 + g] = val * inv_pairs;
+    }
+}
+
 // a2: plane-sweep similarity + softmax -> S_planes [n][D].  All warps of all CTAs spend their time
 // in the projection / gather loops (nothing else competes for registers and shared memory), which
 // is what keeps enough 128-byte feature gathers in flight to load the L2.
@@ -84,12 +147,11 @@ __global__ void __launch_bounds__(128, RN_SIMSCORE_MINB) simscore3_kernel(RnDev 
     __syncthreads();
 
     const float fDm1 = (float)(D - 1);
-    const float inv_pairs = 0.5f / (float)p.npairs;
     const int fshift = p.shift;
 
     const int64_t t = (int64_t)blockIdx.x * 4 + wid;
     if (t >= a.n_rays) return;
-    const int64_t r = rn_tiled_position(t, a.tile_len, p.H, a.tile_mode);
+    const int64_t r = rn_tiled_position(t, a.tile_len, p.H, a.tile_mode & 0xff);
     float rs[3], re[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -135,7 +197,7 @@ __global__ void __launch_bounds__(128, RN_SIMSCORE_MINB) simscore3_kernel(RnDev 
                     fx = (int)(roundf(o0 / nz) + (float)fshift);
                     fy = (int)(roundf(o1 / nz) + (float)fshift);
                 }
-                const int off = rn_feature_offset(p, vbase, fx, fy);
+                const int off = (int)((uint32_t)rn_feature_offset(p, vbase, fx, fy) * 4u);   // BYTE offset (feature volume < 4 GiB)
                 if (kk[h] < D) {
                     sOff[kk[h] * VP + v] = off;
                     if (v == 0) {
@@ -154,66 +216,8 @@ __global__ void __launch_bounds__(128, RN_SIMSCORE_MINB) simscore3_kernel(RnDev 
     __syncwarp();
 
     // ---- step 2: plane scores S_k = 1/2 (|sum_v f_v|^2 - sum_v |f_v|^2) / pairs ----------------------
-    // 8 lanes cover one 32-channel vector (LDG.128 each), 4 planes per warp instruction; views go
-    // in groups of four (one LDS.128 of offsets), slots outside [v_first, V) are predicated off
-    {
-        const int g = lane >> 3;
-        const float *featc = a.features + (lane & 7) * 4;
-        uint64_t r01 = 0, r23 = 0, rq01 = 0, rq23 = 0;
-        const int v_first = ref_same ? 1 : 0;
-        if (ref_same) {
-            const float4 f = __ldg(reinterpret_cast<const float4 *>(featc + ref_off));
-            r01 = rn_pack2(f.x, f.y); r23 = rn_pack2(f.z, f.w);
-            rq01 = rn_fma2(r01, r01, 0); rq23 = rn_fma2(r23, r23, 0);
-        }
-#pragma unroll 2
-        for (int k0 = 0; k0 < D; k0 += 4) {
-            const int k = min(k0 + g, D - 1);
-            const int4 *offk = reinterpret_cast<const int4 *>(sOff + k * VP);
-            uint64_t s01 = r01, s23 = r23, q01 = rq01, q23 = rq23;
-            if constexpr (VT > 0) {
-                constexpr int NG = (VT + 3) / 4;
-                int off[NG * 4];
-#pragma unroll
-                for (int gq = 0; gq < NG; gq++) {
-                    const int4 o4 = offk[gq];
-                    off[4 * gq] = o4.x; off[4 * gq + 1] = o4.y; off[4 * gq + 2] = o4.z; off[4 * gq + 3] = o4.w;
-                }
-                float4 f[VT];
-                if (!ref_same) f[0] = __ldg(reinterpret_cast<const float4 *>(featc + off[0]));
-#pragma unroll
-                for (int v = 1; v < VT; v++) f[v] = __ldg(reinterpret_cast<const float4 *>(featc + off[v]));
-                if (!ref_same) {
-                    const uint64_t f01 = rn_pack2(f[0].x, f[0].y), f23 = rn_pack2(f[0].z, f[0].w);
-                    s01 = rn_add2(s01, f01); s23 = rn_add2(s23, f23);
-                    q01 = rn_fma2(f01, f01, q01); q23 = rn_fma2(f23, f23, q23);
-                }
-#pragma unroll
-                for (int v = 1; v < VT; v++) {
-                    const uint64_t f01 = rn_pack2(f[v].x, f[v].y), f23 = rn_pack2(f[v].z, f[v].w);
-                    s01 = rn_add2(s01, f01); s23 = rn_add2(s23, f23);
-                    q01 = rn_fma2(f01, f01, q01); q23 = rn_fma2(f23, f23, q23);
-                }
-            } else {
-                const int *offs = sOff + k * VP;
-#pragma unroll 4
-                for (int v = v_first; v < V; v++) {
-                    const float4 fv = __ldg(reinterpret_cast<const float4 *>(featc + offs[v]));
-                    const uint64_t f01 = rn_pack2(fv.x, fv.y), f23 = rn_pack2(fv.z, fv.w);
-                    s01 = rn_add2(s01, f01); s23 = rn_add2(s23, f23);
-                    q01 = rn_fma2(f01, f01, q01); q23 = rn_fma2(f23, f23, q23);
-                }
-            }
-            float sx, sy, sz, sw, qx, qy, qz, qw;
-            rn_unpack2(s01, sx, sy); rn_unpack2(s23, sz, sw);
-            rn_unpack2(q01, qx, qy); rn_unpack2(q23, qz, qw);
-            float val = fmaf(sx, sx, fmaf(sy, sy, fmaf(sz, sz, fmaf(sw, sw, -((qx + qy) + (qz + qw))))));
-            val += __shfl_xor_sync(RN_FULL_MASK, val, 1);
-            val += __shfl_xor_sync(RN_FULL_MASK, val, 2);
-            val += __shfl_xor_sync(RN_FULL_MASK, val, 4);
-            if ((lane & 7) == 0 && k0 + g < D) sS[k0 + g] = val * inv_pairs;
-        }
-    }
+    if (ref_same) rn_plane_scores<VT, true>(p, a, sOff, sS, ref_off, lane);
+    else rn_plane_scores<VT, false>(p, a, sOff, sS, ref_off, lane);
     __syncwarp();
 
     // ---- step 3: softmax over the D planes (feature_similarities.cu:109-123) --------------------------

@@ -263,7 +263,8 @@ int rn_engine_bin_rays(const RnParams *p, const int32_t *count, int64_t n_rays, 
 /* One BP sweep over resident state; msgs updated in place, acc_out += messages (bricked grids).
  * order / class_offsets (HOST int64 [rn_num_classes() + 1], may both be NULL): the binning of
  * rn_engine_bin_rays.  first_sweep != 0: messages are taken as all-zero and not read
- * (mrf_np.py:275).  max_count: upper bound on count[] (used when there is no binning). */
+ * (mrf_np.py:275); first_sweep == 2 additionally promises that acc_in holds ONE value everywhere (the
+ * prior right after initialisation, mrf_np.py:285-292), so the sweep does not gather it.  max_count: upper bound on count[] (used when there is no binning). */
 int rn_engine_bp_iteration(const RnParams *p, const int32_t *lin,
                            const int32_t *count, const float *s_hat, float *msgs, const float *acc_in,
                            float *acc_out, const int32_t *order, const int64_t *class_offsets,

@@ -758,6 +758,7 @@ int rn_engine_bp_iteration(const RnParams *p, const int32_t *lin,
     Bp2Args a = {};
     a.lin = lin; a.count = count; a.s_hat = s_hat; a.msgs = msgs; a.acc_in = acc_in;
     a.acc_out = acc_out;
+    a.uniform_acc = (first_sweep == 2) ? 1 : 0;
     if (!order || !class_offsets) {   // no binning: one launch sized for the longest ray
         a.first = 0; a.n = n_rays;
         return launch_bp_class(d, a, first_sweep != 0, (max_count + RN_CHUNK - 1) / RN_CHUNK, S(stream), false);

@@ -97,14 +97,24 @@ __global__ void __launch_bounds__(128) bp4_kernel(RnDev p, Bp2Args a) {
         float *m_row = a.msgs + r * (int64_t)p.row_stride;
 
         // ---- accumulator gathers, lane-consecutive (neighbouring lanes share sectors) -------------
+        // (first sweep straight after a reset: the accumulator is the prior everywhere -- one load)
+        const bool uniform = kFirst && a.uniform_acc;
         float ga[NCH][4];
+        if (uniform) {
+            const float acc0 = __ldg(a.acc_in);
 #pragma unroll
-        for (int c = 0; c < NCH; c++) {
+            for (int c = 0; c < NCH; c++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int i = c * RN_CHUNK + 32 * j + lane;
-                ga[c][j] = 0.f;
-                if (c < NCH - 1 || i < L) ga[c][j] = rn_ld_acc_pol(a.acc_in + sLin[i], pol_keep);
+                for (int j = 0; j < 4; j++) ga[c][j] = acc0;
+        } else {
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int i = c * RN_CHUNK + 32 * j + lane;
+                    ga[c][j] = 0.f;
+                    if (c < NCH - 1 || i < L) ga[c][j] = rn_ld_acc_pol(a.acc_in + sLin[i], pol_keep);
+                }
             }
         }
 

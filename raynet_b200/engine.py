@@ -71,6 +71,7 @@ class RayPotentialEngine(object):
         self.msgs = torch.empty((n, self.R), dtype=torch.float32, **kw)
         self.order = torch.zeros((n,), dtype=torch.int32, **kw)
         self.acc_prev = torch.full((self.GB,), self.prior, dtype=torch.float32, **kw)
+        self._acc_uniform = True         # acc_prev holds the prior everywhere (until a sweep or set_accumulator)
         self.acc_new = torch.empty((self.GB,), dtype=torch.float32, **kw)
         self.axes = torch.zeros((sum(self.grid_shape),), dtype=torch.float32, **kw)
         self._side = None                # side stream + pinned buffer for the class-size read-back
@@ -110,6 +111,7 @@ class RayPotentialEngine(object):
         """Forget the rays; messages count as 0 (the first sweep does not read them) and the
         accumulator is back at the prior (mrf_np.py:275-292)."""
         _lib.call("rn_fill_f32", _ptr(self.acc_prev), self.prior, self.GB, current_stream_ptr())
+        self._acc_uniform = True
         self.launches += 1
         self.iterations_done = 0
         self.n_rays = 0
@@ -227,7 +229,9 @@ class RayPotentialEngine(object):
             ev[0].record()
         _lib.call("rn_engine_bp_iteration", self.params, _ptr(self.lin), _ptr(self.count),
                   _ptr(self.s_hat), _ptr(self.msgs), _ptr(self.acc_prev), _ptr(self.acc_new), _ptr(self.order),
-                  self._class_offsets, 1 if self.iterations_done == 0 else 0, int(self.max_count), self.n_rays, st)
+                  self._class_offsets, (2 if self._acc_uniform else 1) if self.iterations_done == 0 else 0,
+                  int(self.max_count), self.n_rays, st)
+        self._acc_uniform = False
         if self.sweep_events is not None:
             ev[1].record()
             self.sweep_events.append(ev)
@@ -256,6 +260,7 @@ class RayPotentialEngine(object):
             grid = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float32)).to(self.dev)
         grid = grid.reshape(self.grid_shape).contiguous()
         _lib.call("rn_grid_to_bricks", self.params, _ptr(grid), _ptr(self.acc_prev), self.prior, current_stream_ptr())
+        self._acc_uniform = False
         self.launches += 1
 
     def set_messages(self, msgs):

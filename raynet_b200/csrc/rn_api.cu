@@ -764,7 +764,9 @@ int rn_engine_bp_iteration(const RnParams *p, const int32_t *lin,
         return launch_bp_class(d, a, first_sweep != 0, (max_count + RN_CHUNK - 1) / RN_CHUNK, S(stream), false);
     }
     a.order = order;
-    for (int c = 1; c < RN_NCLASS; c++) {   // class 0 (count <= 1) is skipped by BP
+    // one launch per length class, longest rays first (launching the classes alternately on two streams
+    // to fill each other's tails was measured: 3.6 -> 4.1 ms per sweep, the launches compete for L2)
+    for (int c = RN_NCLASS - 1; c >= 1; c--) {   // class 0 (count <= 1) is skipped by BP
         a.first = class_offsets[c];
         a.n = class_offsets[c + 1] - class_offsets[c];
         if (a.first < 0 || a.n < 0 || a.first + a.n > n_rays) return fail(RN_ERR_SHAPE, "class_offsets out of range");

@@ -17,6 +17,11 @@ r, r+N, ... and their 8 neighbours are the same residue class), so per-GPU work 
 
 --impl reference : the CPU implementation of the path (oracle port; see cpu_baseline.kind) on
 the host cores, bounded sample per step.
+
+Extra keys of the N = 1 line (reported baselines / neighbours, none of them part of `value`):
+`cpu_baseline` (the CPU port on ~15 s of the same workload), `gpu_reference` (the reference's OWN CUDA
+kernels, compiled for sm_100a by oracle/build_ref_cuda.py, on this GPU), `cnn` (the MV-CNN feature
+extractor of SURVEY.md 8(f) row 1 on this rank's views).
 """
 import argparse
 import json

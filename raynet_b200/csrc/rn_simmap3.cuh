@@ -1,5 +1,8 @@
-// rn_simmap3.cuh -- front end of the resident pipeline, third version: plane-sweep similarity +
-// softmax (a2) -> plane->voxel interpolation (a4) -> clip_and_renorm, one warp per ray, F = 32.
+// rn_simmap3.cuh -- front end of the resident pipeline, third version, F = 32, one warp per ray, as TWO
+// kernels: simscore3_kernel = plane-sweep similarity + softmax (a2) -> S_planes (256 B per ray);
+// planemap3_kernel = plane->voxel interpolation (a4) + clip_and_renorm -> s_hat, lin.  Split because
+// the similarity is bound by L2->SM gather bandwidth and wants every warp in the gather loop, while
+// the mapping is issue-bound and needs 3 KB of shared memory per ray.
 //
 // simmap_kernel (rn_kernels.cuh, profiles/r01_simmap_source_lines.txt) is instruction-bound: 8300
 // warp instructions per ray at 76 % issue utilisation, a third of them the 576 (plane, view)
@@ -11,11 +14,13 @@
 //     true quotient, so whenever q is further than that from every half-integer it rounds to
 //     the same pixel as the oracle's IEEE quotient; the few samples that are too close (or not
 //     finite) take the exact path.  Integer decisions stay bit-exact, ~10x fewer instructions;
-//   * the feature gathers accumulate with packed FADD2 / FFMA2 (two channels per instruction);
-//     the reference view, whose 64 samples all land on the ray's own pixel, is gathered once;
+//   * the feature gathers accumulate with packed FADD2 / FFMA2 (two channels per instruction), are
+//     addressed with 32-bit byte offsets on a per-lane 64-bit base, and are unrolled per view count
+//     (template VT) so that all V loads of a plane group are in flight together; the reference
+//     view, whose 64 samples all land on the ray's own pixel, is gathered once;
 //   * per-axis tables of voxel-centre coordinates and of bricked accumulator offsets live in
-//     shared memory (one CTA serves RN_SM3_RAYS_PER_WARP rays per warp), the bracket search of
-//     planes_voxels_mapping.cu starts one plane below the answer instead of two.
+//     shared memory (one CTA serves RN_SM3_RAYS_PER_WARP rays per warp), the plane bracket of
+//     planes_voxels_mapping.cu is evaluated in closed form (the interpolant is continuous in t).
 #pragma once
 
 #include "rn_kernels.cuh"

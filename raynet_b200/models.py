@@ -32,6 +32,7 @@ class SimpleCNN(object):
         self._layers = None       # list of dict(kernel, bias, gamma, beta, mean, var) numpy float32
         self._dev = None          # list of (kernel, scale, shift) CUDA tensors
         self.launches = 0
+        self._scratch = None      # two device buffers for the intermediate layers
         self.last_h2d_bytes = 0   # bytes of zero-padded images uploaded by the last predict_features()
 
     # ------------------------------------------------------------------ weights
@@ -97,10 +98,20 @@ class SimpleCNN(object):
         if h < 2 * self.n_layers + 1 or w < 2 * self.n_layers + 1:
             raise AssertionError("input of %d x %d pixels is too small for five valid 3x3 convolutions" % (h, w))
         cin = self.channels
+        # intermediate layers ping-pong between two cached buffers (the first layer's output is the
+        # largest); only the returned feature volume is a fresh tensor
+        need = n * (h - 2) * (w - 2) * self.filters
+        if self._scratch is None or self._scratch[0].numel() < need or self._scratch[0].device != x.device:
+            self._scratch = [torch.empty((need,), dtype=torch.float32, device=x.device) for _ in range(2)]
         for l, (k, scale, shift) in enumerate(self._device_weights()):
-            y = torch.empty((n, h - 2, w - 2, self.filters), dtype=torch.float32, device=x.device)
+            last = l == self.n_layers - 1
+            shape = (n, h - 2, w - 2, self.filters)
+            if last:
+                y = torch.empty(shape, dtype=torch.float32, device=x.device)
+            else:
+                y = self._scratch[l & 1][:n * (h - 2) * (w - 2) * self.filters].view(shape)
             _lib.call("rn_conv3x3_bn_relu", x.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
-                      n, h, w, cin, 1 if l < self.n_layers - 1 else 0, current_stream_ptr())
+                      n, h, w, cin, 0 if last else 1, current_stream_ptr())
             self.launches += 1
             x, h, w, cin = y, h - 2, w - 2, self.filters
         return x

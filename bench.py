@@ -43,6 +43,10 @@ CONFIGS = {
                label="C2 DTU-style 128^3 grid, 5 views, 32 planes, 256x256 px, 3 sweeps"),
     "c3": dict(G=256, V=9, D=64, H=512, W=512, M=768, I=5,
                label="C3 headline 256^3 grid, 9 views, 64 planes, 512x512 px, 5 sweeps"),
+    # BASELINE.json configs[4], meant for 8 GPUs: a ring of 16 cameras, every image with its 14 next neighbours,
+    # two reference images per GPU (the per-ray state of one 1024^2 image at M = 1536 is 19 GB)
+    "c5": dict(G=512, V=15, D=128, H=1024, W=1024, M=1536, I=5, images_per_gpu=2, ring=16,
+               label="C5 aerial-style 512^3 grid, 15 views, 128 planes, 1024x1024 px, 5 sweeps, 2 images per GPU"),
 }
 F, PADDING, GAMMA = 32, 11, 0.05
 METRIC = "rays/s, complete ray-potential inference (front end + I BP sweeps + depth)"
@@ -103,9 +107,16 @@ class FeatureModel(object):
 
 def make_scene(cfg, world):
     from raynet_b200.synth import SyntheticScene
+    if "ring" in cfg:      # fixed ring: neighbours are the next V - 1 cameras, images dealt out round-robin
+        return SyntheticScene(cfg["ring"], cfg["H"], cfg["W"], (cfg["G"],) * 3, neighbors=cfg["V"] - 1, neighbor_stride=1)
     n_total = cfg["V"] * world
     return SyntheticScene(n_total, cfg["H"], cfg["W"], (cfg["G"],) * 3, neighbors=cfg["V"] - 1,
                           neighbor_stride=world)
+
+
+def images_of_rank(cfg, scene, rank, world):
+    imgs = list(range(rank, scene.n_images, world))
+    return imgs[:cfg["images_per_gpu"]] if "images_per_gpu" in cfg else imgs
 
 
 def start_clock_sampler(device_index):
@@ -335,7 +346,7 @@ def run_e2e(args, cfg, scene, model, my_images, rank, world, dev, barrier, total
     gp = GenerationParameters(depth_planes=D, neighbors=V - 1, grid_shape=np.array([G, G, G], np.int32),
                               max_number_of_marched_voxels=M, padding=PADDING, gamma_mrf=GAMMA)
     fp = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, rays_batch=H * W, bp_iterations=I)
-    images_range = (rank, n_total, world)
+    images_range = (rank, n_total, world) if "images_per_gpu" not in cfg else (rank, min(n_total, rank + world * cfg["images_per_gpu"]), world)
 
     def e2e_step():
         maps = list(fp.forward_pass(scene, images_range))
@@ -389,7 +400,7 @@ def run_gpu_arm(args, cfg):
     H, W, G, V, D, M, I = (cfg[k] for k in ("H", "W", "G", "V", "D", "M", "I"))
     scene = make_scene(cfg, world)
     n_total = scene.n_images
-    my_images = list(range(rank, n_total, world))              # this rank's reference images
+    my_images = images_of_rank(cfg, scene, rank, world)          # this rank's reference images
     my_views = sorted(set(v for i in my_images for v in scene.view_order(i)))
     model = FeatureModel(my_views, H, W)
     n_rays = len(my_images) * H * W
@@ -466,7 +477,7 @@ def run_gpu_arm(args, cfg):
     sum_L = int(counts[counts > 1].sum().item())
     mean_L = float(counts.float().mean().item())
     max_L = int(eng.max_count)
-    total_rays = n_rays * world
+    total_rays = n_rays * world        # every rank holds the same number of images in the configurations above
     value = total_rays / (ms_step * 1e-3)
 
     e2e = None
@@ -513,7 +524,7 @@ def run_gpu_arm(args, cfg):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic or {}).get("bp_kernel_dram_bytes_per_launch"),
+                "traffic": (traffic or {}).get("bp_kernel_dram_bytes_per_launch") if args.config == "c3" else None,
                 "kernel": "bp4_kernel (one BP sweep over all rays of this rank = one launch per ray-length class)",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": sweep_avg_ms,
                 "launches_timed": len(sweep_ms), "peak_source": peak_src,

@@ -28,6 +28,9 @@
 #ifndef RN_SIMSCORE_MINB
 #define RN_SIMSCORE_MINB 8
 #endif
+#ifndef RN_SIMSCORE_UNROLL
+#define RN_SIMSCORE_UNROLL 2     // plane groups (of 4 planes x V gathers) in flight per warp
+#endif
 #ifndef RN_SM3_RAYS_PER_WARP
 #define RN_SM3_RAYS_PER_WARP 4
 #endif
@@ -87,7 +90,8 @@ __device__ __forceinline__ void rn_plane_scores(const RnDev &p, const SimMapArgs
         rq01 = rn_fma2(r01, r01, 0); rq23 = rn_fma2(r23, r23, 0);
     }
     constexpr int V0 = kRef ? 1 : 0;
-#pragma unroll 2
+    constexpr int kUnroll = RN_SIMSCORE_UNROLL;
+#pragma unroll kUnroll
     for (int k0 = 0; k0 < D; k0 += 4) {
         const int k = min(k0 + g, D - 1);
         uint64_t s01 = r01, s23 = r23, q01 = rq01, q23 = rq23;

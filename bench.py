@@ -19,9 +19,9 @@ r, r+N, ... and their 8 neighbours are the same residue class), so per-GPU work 
 the host cores, bounded sample per step.
 
 Extra keys of the N = 1 line (reported baselines / neighbours, none of them part of `value`):
-`cpu_baseline` (the CPU port on ~15 s of the same workload), `gpu_reference` (the reference's OWN CUDA
-kernels, compiled for sm_100a by oracle/build_ref_cuda.py, on this GPU), `cnn` (the MV-CNN feature
-extractor of SURVEY.md 8(f) row 1 on this rank's views).
+`cpu_baseline` (the CPU port on ~15 s of the same workload) and `cnn` (the MV-CNN feature extractor of
+SURVEY.md 8(f) row 1 on this rank's views).  The speed of the reference's OWN CUDA kernels on the same GPU
+is measured by tests/test_gpu_ref_cuda.py::test_reference_cuda_speed_bar (only tests may run oracle/_ref/cuda).
 """
 import argparse
 import json
@@ -218,54 +218,6 @@ def cpu_timed_passes(sample, target_s):
         rays += int(sample.ray_idxs.shape[0])
         passes += 1
     return rays, secs, passes
-
-
-def reference_cuda_bar(cfg, scene, model, my_views, dev):
-    """The reference's OWN CUDA kernels (cuda_implementations/*.cu + raynet_fp.py, compiled for sm_100a
-    by oracle/build_ref_cuda.py) on this GPU: one reference image through `batch_raynet_fp` (front end +
-    one BP sweep, what the reference launches per image per sweep, forward_pass.py:650-663) and through
-    `batch_complete_depth_estimation` (:723-736), timed with CUDA events; a complete inference of the
-    reference is I x images fp launches + images de launches.  Reported next to ours, not a target."""
-    import torch
-    from oracle import ref_cuda
-    from raynet_b200.synth import camera_arrays
-    name = [k for k, v in CONFIGS.items() if v is cfg][0]
-    if not ref_cuda.available(name):
-        return None
-    H, W, G, V, D, M, I = (cfg[k] for k in ("H", "W", "G", "V", "D", "M", "I"))
-    ref = ref_cuda.RefCuda(name)
-    order = scene.view_order(0)
-    P, P_inv, centre = camera_arrays([scene.get_image(j) for j in order])
-    feats = model.host[torch.tensor([my_views.index(v) for v in order])].to(dev).contiguous()
-    n = H * W
-    ins = [torch.arange(n, dtype=torch.int32, device=dev), feats.reshape(-1), torch.from_numpy(P).to(dev).reshape(-1),
-           torch.from_numpy(P_inv).to(dev).reshape(-1), torch.from_numpy(centre).to(dev).reshape(-1),
-           torch.from_numpy(np.ascontiguousarray(scene.voxel_grid().transpose(1, 2, 3, 0))).to(dev).reshape(-1)]
-    prior = float(np.float32(np.log(GAMMA) - np.log(1 - GAMMA)))
-    idx = torch.zeros((n, M, 3), dtype=torch.int32, device=dev)
-    cnt = torch.zeros((n,), dtype=torch.int32, device=dev)
-    S = torch.zeros((n, M), dtype=torch.float32, device=dev)
-    msgs = torch.zeros((n, M), dtype=torch.float32, device=dev)
-    acc_in = torch.full((G, G, G), prior, dtype=torch.float32, device=dev)
-    acc_out = torch.full((G, G, G), prior, dtype=torch.float32, device=dev)
-    depth = torch.zeros((n,), dtype=torch.float32, device=dev)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    ref.raynet_fp(*ins, idx, cnt, S, acc_in, msgs, acc_out)      # warm-up (module load, caches)
-    torch.cuda.synchronize()
-    ev[0].record()
-    ref.raynet_fp(*ins, idx, cnt, S, acc_in, msgs, acc_out)
-    ev[1].record()
-    ref.raynet_de(*ins, idx, cnt, S, acc_out, msgs, depth)
-    ev[2].record()
-    torch.cuda.synchronize()
-    t_fp, t_de = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
-    n_img = V
-    total_ms = n_img * (I * t_fp + t_de)
-    return {"value": n_img * n / (total_ms * 1e-3), "unit": "rays/s", "kind": "reference CUDA kernels, sm_100a build",
-            "fp_launch_ms": t_fp, "de_launch_ms": t_de,
-            "sample": "1 of %d reference images timed (%d rays, 256 threads/block): batch_raynet_fp %.1f ms, "
-                      "batch_complete_depth_estimation %.1f ms; value = rays / (images x (%d sweeps x fp + de)), "
-                      "host loop and transfers of forward_pass.py excluded" % (n_img, n, t_fp, t_de, I)}
 
 
 def cnn_bar(cfg, dev, n_views):
@@ -484,13 +436,6 @@ def run_gpu_arm(args, cfg):
     if not args.no_e2e:
         e2e = run_e2e(args, cfg, scene, model, my_images, rank, world, dev, barrier, total_rays)
     del eng, feats
-    gpu_ref = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        torch.cuda.empty_cache()
-        try:
-            gpu_ref = reference_cuda_bar(cfg, scene, model, my_views, dev)
-        except Exception as e:      # a reported extra, never a reason to lose the bench line
-            gpu_ref = {"unavailable": repr(e)}
     cnn = None
     if rank == 0 and not args.no_cpu:
         torch.cuda.empty_cache()
@@ -535,8 +480,6 @@ def run_gpu_arm(args, cfg):
                           "depth": float(stages[:, 2].mean())},
             "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
         }
-        if gpu_ref is not None:
-            line["gpu_reference"] = gpu_ref
         if cnn is not None:
             line["cnn"] = cnn
         if world == 1 and not args.no_cpu:

@@ -110,3 +110,79 @@ def test_against_reference_cuda_kernels(torch_cuda, oracle, name, mk):
     dr, dg = d_ref.cpu().numpy(), d_got.cpu().numpy()
     assert decided.sum() > 0.8 * bp.sum()
     assert np.abs(dr[decided] - dg[decided]).max() < 1e-5
+
+
+def test_reference_cuda_speed_bar(torch_cuda):
+    """The "reference kernel on the same box" bar of SURVEY.md 8d: one reference image of the headline
+    configuration C3 through the reference's own `batch_raynet_fp` (front end + one BP sweep: what the
+    reference launches per image per sweep, forward_pass.py:650-663) and `batch_complete_depth_estimation`
+    (:723-736), timed with CUDA events; a complete inference of the reference is I x images fp launches +
+    images de launches.  Prints the figure quoted in profiles/README.md and checks that the resident
+    pipeline is at least an order of magnitude faster on the same workload."""
+    import json
+    import os
+    torch = torch_cuda
+    import bench
+    from oracle import ref_cuda
+    from raynet_b200.engine import RayPotentialEngine
+    from raynet_b200.synth import camera_arrays
+    if not ref_cuda.available("c3"):
+        pytest.skip("oracle/_ref/cuda/raynet_fp_c3.cubin not built")
+    cfg = bench.CONFIGS["c3"]
+    H, W, G, V, D, M, I = (cfg[k] for k in ("H", "W", "G", "V", "D", "M", "I"))
+    dev = torch.device("cuda")
+    scene = bench.make_scene(cfg, 1)
+    order = scene.view_order(0)
+    P, P_inv, centre = camera_arrays([scene.get_image(j) for j in order])
+    feats = torch.stack([bench.view_features(v, H, W) for v in order]).to(dev).contiguous()
+    n = H * W
+    ids = torch.arange(n, dtype=torch.int32, device=dev)
+    dP, dPi, dC = torch.from_numpy(P).to(dev), torch.from_numpy(P_inv).to(dev), torch.from_numpy(centre).to(dev)
+    vgrid = torch.from_numpy(np.ascontiguousarray(scene.voxel_grid().transpose(1, 2, 3, 0))).to(dev)
+    ref = ref_cuda.RefCuda("c3")
+    ins = [ids, feats.reshape(-1), dP.reshape(-1), dPi.reshape(-1), dC.reshape(-1), vgrid.reshape(-1)]
+    idx = torch.zeros((n, M, 3), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((n,), dtype=torch.int32, device=dev)
+    S = torch.zeros((n, M), dtype=torch.float32, device=dev)
+    msgs = torch.zeros((n, M), dtype=torch.float32, device=dev)
+    acc_in = torch.full((G, G, G), PRIOR, dtype=torch.float32, device=dev)
+    acc_out = torch.full((G, G, G), PRIOR, dtype=torch.float32, device=dev)
+    depth = torch.zeros((n,), dtype=torch.float32, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ref.raynet_fp(*ins, idx, cnt, S, acc_in, msgs, acc_out)          # warm-up
+    torch.cuda.synchronize()
+    ev[0].record()
+    ref.raynet_fp(*ins, idx, cnt, S, acc_in, msgs, acc_out)
+    ev[1].record()
+    ref.raynet_de(*ins, idx, cnt, S, acc_out, msgs, depth)
+    ev[2].record()
+    torch.cuda.synchronize()
+    t_fp, t_de = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    ref_rays_per_s = V * n / (V * (I * t_fp + t_de) * 1e-3)
+    del idx, S, msgs
+    # ours: the same image through the resident pipeline (front end + I sweeps + depth)
+    eng = RayPotentialEngine(M, D, V, bench.F, H, W, bench.PADDING, scene.bbox.ravel(), (G, G, G), gamma=bench.GAMMA,
+                             max_rays=n, use_distributed=False)
+    eng.set_voxel_grid(scene.voxel_grid())
+
+    def ours():
+        eng.reset()
+        eng.add_image(ids, feats, dP, dPi, dC)
+        eng.run_bp(I)
+        return eng.depth()
+
+    ours()
+    torch.cuda.synchronize()
+    ev[0].record()
+    d_ours = ours()
+    ev[1].record()
+    torch.cuda.synchronize()
+    ours_rays_per_s = n / (ev[0].elapsed_time(ev[1]) * 1e-3)
+    out = {"reference_cuda_rays_per_s": ref_rays_per_s, "fp_launch_ms": t_fp, "de_launch_ms": t_de,
+           "ours_rays_per_s_one_image": ours_rays_per_s, "ratio": ours_rays_per_s / ref_rays_per_s,
+           "what": "C3, one reference image (%d rays); reference = its own CUDA kernels built for sm_100a, %d sweeps x fp + de" % (n, I)}
+    print("reference CUDA speed bar: " + json.dumps(out))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open(os.path.join("gpurun_out", "ref_cuda_speed_bar.json"), "w"), indent=1)
+    assert np.isfinite(d_ours.cpu().numpy()).all()
+    assert ours_rays_per_s > 10 * ref_rays_per_s

@@ -18,8 +18,12 @@
 
 #include "rn_bp3.cuh"
 
+#ifndef RN_POL_ROWS
+#define RN_POL_ROWS 1     // evict-first hint on the prefetched rows
+#endif
 __device__ __forceinline__ void rn_cp_async16(uint32_t dst_smem, const void *src, uint64_t pol) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(pol) : "memory");
+    if (RN_POL_ROWS) asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(pol) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 __device__ __forceinline__ void rn_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

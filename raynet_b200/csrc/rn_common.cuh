@@ -88,13 +88,18 @@ __device__ __forceinline__ void rn_red_add(float *p, float v) {
     asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
 }
 // The same two with a caller-held policy descriptor (created once per kernel).
+#ifndef RN_POL_ACC
+#define RN_POL_ACC 3      // bit 0: evict-last hint on the accumulator gathers, bit 1: on the scatter-adds
+#endif
 __device__ __forceinline__ float rn_ld_acc_pol(const float *p, uint64_t pol) {
     float v;
-    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    if (RN_POL_ACC & 1) asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void rn_red_add_pol(float *p, float v, uint64_t pol) {
-    asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
+    if (RN_POL_ACC & 2) asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
+    else asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
 }
 
 // ---- warp scans ------------------------------------------------------------------------

@@ -128,3 +128,30 @@ def test_dataset_on_disk_to_point_cloud(torch_cuda, tmp_path):
     assert plain.shape[1] == n * (H - 4) * (W - 4) and pts.shape[1] <= plain.shape[1]
     # every fused point lies on its pixel's ray at the predicted depth: inside the bounding box (+ one voxel)
     assert (np.abs(plain) <= 1.0 + 2.0 / G + 1e-4).all()
+
+
+def test_forward_pass_with_filtered_rays(torch_cuda):
+    """filter_out_rays=True (forward_pass.py:168-179): only pixels with ground truth become rays; the
+    others come back as 0 in the depth map, the rest are positive and finite."""
+    from raynet_b200.common.generation_parameters import GenerationParameters
+    from raynet_b200.forward_pass import get_forward_pass_factory
+    from raynet_b200.synth import SyntheticScene, random_features
+    V, H, W, G, D, M = 3, 24, 20, 24, 8, 72
+    scene = SyntheticScene(V, H, W, (G, G, G), with_images=True)
+    rng = np.random.RandomState(3)
+    gt = [(rng.rand(H, W) > 0.4).astype(np.float32) * 2.0 for _ in range(V)]
+    scene.get_depth_map = lambda i: gt[i]
+    feats = random_features(V, H, W, 32, 11, seed=4)
+
+    class Model(object):
+        def predict_features(self, scene, views):
+            return feats[list(views)]
+
+    gp = GenerationParameters(depth_planes=D, neighbors=V - 1, grid_shape=np.array([G, G, G], np.int32),
+                              max_number_of_marched_voxels=M, padding=11, gamma_mrf=0.05)
+    fp = get_forward_pass_factory("raynet")(Model(), gp, "sample_in_bbox", scene.image_shape, H * W, filter_out_rays=True)
+    maps = list(fp.forward_pass(scene, (0, V, 1)))
+    for k, m in enumerate(maps):
+        assert m.shape == (H, W)
+        assert (m[gt[k] == 0] == 0).all()
+        assert np.isfinite(m).all() and (m[gt[k] != 0] > 0).all()

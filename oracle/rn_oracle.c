@@ -26,7 +26,7 @@
  *   - sample_in_bbox, similarity, arg-max depth have NO CPU twin and no test in the
  *     reference: they are restated from the .cu text and pinned on the GPU box against an
  *     EXECUTION of the reference's own CUDA kernels (oracle/build_ref_cuda.py compiles
- *     cuda_implementations/*.cu + the kernel text of raynet_fp.py for sm_100a,
+ *     the .cu files of cuda_implementations/ + the kernel text of raynet_fp.py for sm_100a,
  *     tests/test_gpu_ref_cuda.py runs them next to the sm_100a kernels and this oracle's
  *     outputs: voxel lists identical, distributions / messages / S_new within 1e-5).
  */

@@ -282,24 +282,28 @@ class RayNetForwardPass(ForwardPass):
         slot = dict((v, k) for k, v in enumerate(views))
         f_host = self._view_features(scene, views)
         main = torch.cuda.current_stream(dev)
+        copied = {}       # view slot -> event after which its feature map is on the device
         if f_host.is_cuda:
             # the model produced the feature volume on the device (raynet_b200.models.SimpleCNN): nothing to upload
             self._feat_dev = f_host.contiguous()
-            copied = torch.cuda.Event()
-            copied.record(main)
             self.h2d_bytes += int(getattr(self._model, "last_h2d_bytes", 0))
         else:
             if self._feat_dev is None or self._feat_dev.shape != f_host.shape:
                 self._feat_dev = torch.empty(f_host.shape, dtype=torch.float32, device=dev)
-            # the feature maps travel on a copy stream while the rays are traced and binned (neither
-            # needs them); the similarity kernels wait for the copy
+            # the feature maps travel on a copy stream, view by view in the order the reference images
+            # need them, while the rays are traced and binned (neither needs them); the similarity of an
+            # image waits only for the views it reads
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=dev)
             self._copy_stream.wait_stream(main)      # the previous call's readers of _feat_dev are done
+            first_use = []
+            for o in orders:
+                first_use += [slot[v] for v in o if slot[v] not in first_use]
             with torch.cuda.stream(self._copy_stream):
-                self._feat_dev.copy_(f_host, non_blocking=True)
-                copied = torch.cuda.Event()
-                copied.record()
+                for k in first_use:
+                    self._feat_dev[k].copy_(f_host[k], non_blocking=True)
+                    copied[k] = torch.cuda.Event()
+                    copied[k].record()
             self.h2d_bytes += f_host.numel() * 4
         if self.engine is None or self.engine.capacity < total:
             self.engine = self._make_engine(scene, f_host.shape[-1], total)
@@ -333,8 +337,10 @@ class RayNetForwardPass(ForwardPass):
         self.engine.finalize_frontend()
         self.d2h_bytes += 4
         # ---- front end, second half: similarity + plane->voxel mapping per reference image -----
-        main.wait_event(copied)
         for k, (P_dev, view_ids) in enumerate(per_image):
+            for v in orders[k]:
+                if slot[v] in copied:
+                    main.wait_event(copied.pop(slot[v]))
             self.engine.score_image(k, self._feat_dev, P_dev, view_ids=view_ids, n_feature_slots=len(views))
         # ---- BP sweeps + depth -----------------------------------------------------------------
         self.engine.run_bp(self.bp_iterations)

@@ -1,22 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- rays/s of complete ray-potential inference (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--config c3] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--config c3] [--scaling strong|weak] [--impl reference]
     (N > 1: launched by torchrun, one rank per GPU, NCCL)
 
-One "step" = one complete inference over this rank's reference images:
-    front end (sample_in_bbox + plane-sweep similarity + DDA + plane->voxel) once per image,
+One "step" = one complete inference over the job:
+    front end (sample_in_bbox + plane-sweep similarity + DDA + plane->voxel) once per ray,
     I synchronous BP sweeps over all rays (+ one all-reduce of the occupancy accumulator per
     sweep when N > 1), one depth pass (+ arg-max -> depth).
+Scaling.  BASELINE.json configs[3] is "the 256^3 workload sharded by ray batch across 2/4/8 GPUs":
+    STRONG scaling (default for c1/c2/c3) -- the job is fixed (C3: 9 reference images x 512 x 512 rays); the
+    (image, column-major pixel) ray enumeration is cut into N contiguous blocks (raynet_b200/sharding.py),
+    so a rank owns whole and partial images.  --scaling weak (default for c5, whose 16 images only fit on
+    8 GPUs): every rank owns the same number of whole reference images.
 `value`  : rays/s, whole job, inputs (feature maps, cameras, ray ids) resident in HBM.
 `e2e`    : the same through the reference-facing plug-in call
-           RayNetForwardPass.forward_pass(scene, images_range) with PINNED HOST feature maps in
-           and HOST depth maps out (H2D / D2H inside the timed region).
-Weak scaling: every rank owns 9 reference images (a ring of 9*N cameras; rank r owns images
-r, r+N, ... and their 8 neighbours are the same residue class), so per-GPU work is fixed.
+           RayNetForwardPass.forward_pass(scene, images_range) with HOST IMAGES in (zero-padded views from
+           pinned memory -> MV-CNN on the device, raynet_b200.models.SimpleCNN) and HOST depth maps out
+           (H2D / D2H inside the timed region), timed over all --steps.
+`roofline`: the BP sweep (bp4_kernel), first and non-first sweeps separately (a first sweep moves 12 B per
+           traversed voxel, the others 20 B: SURVEY.md 8d), plus per-stage entries for the front end and
+           the depth pass against the same byte model.
 
 --impl reference : the CPU implementation of the path (oracle port; see cpu_baseline.kind) on
-the host cores, bounded sample per step.
+the host cores (all of them, also under torchrun), bounded sample per step.
 
 Extra keys of the N = 1 line (reported baselines / neighbours, none of them part of `value`):
 `cpu_baseline` (the CPU port on ~15 s of the same workload) and `cnn` (the MV-CNN feature extractor of
@@ -62,12 +69,21 @@ def measured_peak():
 
 
 def profiled_traffic():
-    """dram bytes per sweep-kernel launch from the committed ncu capture, if any."""
+    """DRAM bytes of one non-first BP sweep from the committed ncu capture of this configuration
+    (profiles/roofline_traffic.json).  NOT measured by this run -- ncu cannot run inside the timed
+    region; the line says so next to the number."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             return json.load(f)
     except Exception:
         return None
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 # ------------------------------------------------------------------------------------------
@@ -105,18 +121,40 @@ class FeatureModel(object):
         return self.host[torch.tensor([self.views.index(v) for v in view_indices])]
 
 
-def make_scene(cfg, world):
+def scaling_of(args, cfg):
+    if args.scaling:
+        return args.scaling
+    return "weak" if "images_per_gpu" in cfg else "strong"
+
+
+def make_scene(cfg, world, scaling="weak", with_images=False):
+    """strong: the fixed job (a ring of V cameras, every view a reference image with the others as neighbours;
+    c5: its ring of 16).  weak: V reference images per GPU on a ring of V * world cameras (rank r owns images
+    r, r + world, ... whose neighbours are the same residue class)."""
     from raynet_b200.synth import SyntheticScene
     if "ring" in cfg:      # fixed ring: neighbours are the next V - 1 cameras, images dealt out round-robin
-        return SyntheticScene(cfg["ring"], cfg["H"], cfg["W"], (cfg["G"],) * 3, neighbors=cfg["V"] - 1, neighbor_stride=1)
+        return SyntheticScene(cfg["ring"], cfg["H"], cfg["W"], (cfg["G"],) * 3, neighbors=cfg["V"] - 1, neighbor_stride=1,
+                              with_images=with_images)
+    if scaling == "strong":
+        return SyntheticScene(cfg["V"], cfg["H"], cfg["W"], (cfg["G"],) * 3, neighbors=cfg["V"] - 1, neighbor_stride=1,
+                              with_images=with_images)
     n_total = cfg["V"] * world
     return SyntheticScene(n_total, cfg["H"], cfg["W"], (cfg["G"],) * 3, neighbors=cfg["V"] - 1,
-                          neighbor_stride=world)
+                          neighbor_stride=world, with_images=with_images)
 
 
-def images_of_rank(cfg, scene, rank, world):
+def segments_of_rank(cfg, scene, rank, world, scaling):
+    """This rank's share of the job as [(image, first ray, last ray)]."""
+    from raynet_b200 import sharding
+    H, W = cfg["H"], cfg["W"]
+    if scaling == "strong":
+        n = scene.n_images
+        unit = 64 * H if (H * W) % (64 * H) == 0 else (8 * H if (H * W) % (8 * H) == 0 else 1)
+        return sharding.image_segments([H * W] * n, rank, world, unit)
     imgs = list(range(rank, scene.n_images, world))
-    return imgs[:cfg["images_per_gpu"]] if "images_per_gpu" in cfg else imgs
+    if "images_per_gpu" in cfg:
+        imgs = imgs[:cfg["images_per_gpu"]]
+    return [(i, 0, H * W) for i in imgs]
 
 
 def start_clock_sampler(device_index):
@@ -172,7 +210,7 @@ class CpuSample(object):
         from raynet_b200.synth import camera_arrays
         self.orc = orc
         self.cfg = cfg
-        scene = make_scene(cfg, 1)
+        scene = make_scene(cfg, 1, "strong")
         H, W = cfg["H"], cfg["W"]
         order = scene.view_order(0)
         self.P, self.P_inv, self.centre = camera_arrays([scene.get_image(j) for j in order])
@@ -258,12 +296,15 @@ def cnn_bar(cfg, dev, n_views):
 
 
 def run_reference_arm(args, cfg):
-    """--impl reference: the CPU implementation on the host cores (rank 0 only)."""
+    """--impl reference: the CPU implementation on the host cores (rank 0 only; the other ranks exit).
+    torchrun exports OMP_NUM_THREADS=1 to its workers: the thread count is set explicitly to every core
+    this process may run on, so the arm is the same at every N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as orc
     orc.build()
+    orc.set_threads(host_cores())
     cores = orc.num_threads()
     sample = cpu_calibrated_sample(cfg, 3.0)
     for _ in range(args.warmup):
@@ -276,8 +317,8 @@ def run_reference_arm(args, cfg):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["label"], "rays_per_step": n, "host": "CPU only"},
+        "scaling": scaling_of(args, cfg), "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["label"], "rays_per_step": n, "host": "CPU only, %d threads" % cores},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": desc,
                          "note": "OpenMP C restatement of the reference's numpy/Cython/.cu path (oracle/rn_oracle.c); "
                                  "the reference's own CPU code is single-threaded Python loops"},
@@ -287,40 +328,53 @@ def run_reference_arm(args, cfg):
     print(json.dumps(line), flush=True)
 
 
-def run_e2e(args, cfg, scene, model, my_images, rank, world, dev, barrier, total_rays):
-    """e2e arm: reference-facing plug-in call, host buffers in and out."""
+def run_e2e(args, cfg, rank, world, dev, barrier, total_rays, scaling):
+    """e2e arm: the reference-facing plug-in call with HOST buffers: images in (pinned zero-padded views ->
+    MV-CNN on the device), host depth maps out; every --steps step timed."""
     import torch
     import torch.distributed as dist
     from raynet_b200.common.generation_parameters import GenerationParameters
     from raynet_b200.forward_pass import RayNetForwardPass
+    from raynet_b200.models import SimpleCNN
     H, W, G, V, D, M, I = (cfg[k] for k in ("H", "W", "G", "V", "D", "M", "I"))
+    scene = make_scene(cfg, world, scaling, with_images=True)
     n_total = scene.n_images
+    model = SimpleCNN.random_init(channels=3, seed=0)
     gp = GenerationParameters(depth_planes=D, neighbors=V - 1, grid_shape=np.array([G, G, G], np.int32),
                               max_number_of_marched_voxels=M, padding=PADDING, gamma_mrf=GAMMA)
-    fp = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, rays_batch=H * W, bp_iterations=I)
-    images_range = (rank, n_total, world) if "images_per_gpu" not in cfg else (rank, min(n_total, rank + world * cfg["images_per_gpu"]), world)
+    if scaling == "strong":
+        fp = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, rays_batch=H * W, bp_iterations=I,
+                               shard="rays")
+        images_range = (0, n_total, 1)
+        n_maps = n_total
+    else:
+        fp = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, rays_batch=H * W, bp_iterations=I,
+                               shard="images")
+        stop = n_total if "images_per_gpu" not in cfg else min(n_total, rank + world * cfg["images_per_gpu"])
+        images_range = (rank, stop, world)
+        n_maps = len(range(rank, stop, world))
 
     def e2e_step():
         maps = list(fp.forward_pass(scene, images_range))
-        assert len(maps) == len(my_images) and maps[0].shape == (H, W)
+        assert len(maps) == n_maps and maps[0].shape == (H, W)
         return maps
 
     for _ in range(2):
         e2e_step()
-    e2e_steps = max(2, min(args.steps, 5))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(args.steps):
         e2e_step()
     barrier()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
-    return {"value": total_rays / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
+    return {"value": total_rays / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms, "steps_timed": args.steps,
             "h2d_bytes_per_step": int(fp.h2d_bytes), "d2h_bytes_per_step": int(fp.d2h_bytes),
-            "api": "raynet_b200.forward_pass.RayNetForwardPass.forward_pass(scene, images_range), pinned host "
-                   "feature maps in, host depth maps out; host wall clock around the call"}
+            "api": "raynet_b200.forward_pass.RayNetForwardPass.forward_pass(scene, images_range): zero-padded host "
+                   "images in (pinned) -> SimpleCNN on the device -> ray-potential inference -> host depth maps "
+                   "out; host wall clock around the call, barrier + synchronize on both sides, max over ranks"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -343,19 +397,18 @@ def run_gpu_arm(args, cfg):
         print("[bench] note: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
 
     from raynet_b200 import _lib
-    from raynet_b200.common.generation_parameters import GenerationParameters
     from raynet_b200.engine import RayPotentialEngine
-    from raynet_b200.forward_pass import RayNetForwardPass
     from raynet_b200.synth import camera_arrays
     _lib.load()
 
+    scaling = scaling_of(args, cfg)
     H, W, G, V, D, M, I = (cfg[k] for k in ("H", "W", "G", "V", "D", "M", "I"))
-    scene = make_scene(cfg, world)
-    n_total = scene.n_images
-    my_images = images_of_rank(cfg, scene, rank, world)          # this rank's reference images
+    scene = make_scene(cfg, world, scaling)
+    segs = segments_of_rank(cfg, scene, rank, world, scaling)       # this rank's (image, first ray, last ray)
+    my_images = sorted(set(i for (i, _, _) in segs))
     my_views = sorted(set(v for i in my_images for v in scene.view_order(i)))
     model = FeatureModel(my_views, H, W)
-    n_rays = len(my_images) * H * W
+    n_rays = int(sum(b - a for (_, a, b) in segs))
     dev = torch.device("cuda", local)
 
     # ---------------- device-resident arm -------------------------------------------------------
@@ -363,14 +416,14 @@ def run_gpu_arm(args, cfg):
     eng.set_voxel_grid(scene.voxel_grid())
     feats = model.host.to(dev)
     slot = dict((v, k) for k, v in enumerate(my_views))
-    per_image = []
+    per_seg = []
     ids = torch.arange(H * W, dtype=torch.int32, device=dev)
-    for i in my_images:
+    for (i, a, b) in segs:
         order = scene.view_order(i)
         P, P_inv, centre = camera_arrays([scene.get_image(j) for j in order])
-        per_image.append((torch.from_numpy(P).to(dev), torch.from_numpy(P_inv).to(dev),
-                          torch.from_numpy(centre).to(dev),
-                          torch.tensor([slot[v] for v in order], dtype=torch.int32, device=dev)))
+        per_seg.append((ids[a:b], torch.from_numpy(P).to(dev), torch.from_numpy(P_inv).to(dev),
+                        torch.from_numpy(centre).to(dev),
+                        torch.tensor([slot[v] for v in order], dtype=torch.int32, device=dev)))
     stage_events = []
 
     def device_step(record=False):
@@ -378,12 +431,12 @@ def run_gpu_arm(args, cfg):
         if record:
             ev[0].record()
         eng.reset()
-        # same order as RayNetForwardPass.forward_pass: trace every image, bin the rays (the class sizes
-        # travel to the host on a side stream meanwhile), then similarity + mapping per image
-        for (P, P_inv, centre, vids) in per_image:
-            eng.trace_image(ids, P_inv, centre)
+        # same order as RayNetForwardPass.forward_pass: trace every segment, bin the rays (the class sizes
+        # travel to the host on a side stream meanwhile), then similarity + mapping per segment
+        for (sid, P, P_inv, centre, vids) in per_seg:
+            eng.trace_image(sid, P_inv, centre)
         eng.finalize_frontend()
-        for k, (P, P_inv, centre, vids) in enumerate(per_image):
+        for k, (sid, P, P_inv, centre, vids) in enumerate(per_seg):
             eng.score_image(k, feats, P, view_ids=vids, n_feature_slots=len(my_views))
         if record:
             ev[1].record()
@@ -420,22 +473,26 @@ def run_gpu_arm(args, cfg):
     eng.sweep_events = []
     launches0 = eng.launches
     ms_step = timed(lambda: device_step(record=True), args.steps)
-    gpu_launches = eng.launches - launches0
-    sweep_ms = [a.elapsed_time(b) for (a, b) in eng.sweep_events]
+    gpu_launches = (eng.launches - launches0) // args.steps
+    sweep_ms = np.array([a.elapsed_time(b) for (a, b) in eng.sweep_events]).reshape(args.steps, I)
     eng.sweep_events = None
     clocks = stop_clock_sampler(proc, path) if rank == 0 else None
     stages = np.array([[e[k].elapsed_time(e[k + 1]) for k in range(3)] for e in stage_events])
     counts = eng.count[:eng.n_rays]
     sum_L = int(counts[counts > 1].sum().item())
-    mean_L = float(counts.float().mean().item())
+    mean_L = float(counts.float().mean().item()) if eng.n_rays else 0.0
     max_L = int(eng.max_count)
-    total_rays = n_rays * world        # every rank holds the same number of images in the configurations above
+    totals = torch.tensor([n_rays], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(totals)
+    total_rays = int(totals.item())
     value = total_rays / (ms_step * 1e-3)
 
     e2e = None
+    del eng, feats, model
+    torch.cuda.empty_cache()
     if not args.no_e2e:
-        e2e = run_e2e(args, cfg, scene, model, my_images, rank, world, dev, barrier, total_rays)
-    del eng, feats
+        e2e = run_e2e(args, cfg, rank, world, dev, barrier, total_rays, scaling)
     cnn = None
     if rank == 0 and not args.no_cpu:
         torch.cuda.empty_cache()
@@ -446,38 +503,66 @@ def run_gpu_arm(args, cfg):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        # dominant kernel: the BP sweep.  Algorithmic bytes per launch = 20 B per traversed voxel
-        # (s_hat 4 + msg in 4 + msg out 4 + acc gather 4 + acc scatter-add 4)
-        sweep_avg_ms = float(np.mean(sweep_ms))
-        bytes_per_launch = 20.0 * sum_L
-        achieved = bytes_per_launch / (sweep_avg_ms * 1e-3) / 1e9
-        traffic = profiled_traffic()
-        # whole-step byte model of SURVEY.md 8d, for context
-        feat_share = len(my_views) * (H + PADDING + 1) * (W + PADDING + 1) * F * 4.0
-        step_bytes = sum_L * (20.0 * I + 16.0) + 28.0 * n_rays + feat_share + I * 3 * G ** 3 * 4.0
+        # dominant kernel: the BP sweep.  Algorithmic bytes per traversed voxel: a non-first sweep
+        # moves s_hat 4 + msg in 4 + msg out 4 + acc gather 4 + acc scatter-add 4 = 20 B; the first sweep after
+        # a reset reads no messages and gathers nothing (the accumulator is the prior everywhere) = 12 B
+        first_ms = float(sweep_ms[:, 0].mean())
+        next_ms = float(sweep_ms[:, 1:].mean()) if I > 1 else first_ms
+        b_first, b_next = 12.0 * sum_L, 20.0 * sum_L
+        a_next = b_next / (next_ms * 1e-3) / 1e9
+        a_first = b_first / (first_ms * 1e-3) / 1e9
+        blend_bytes = b_first + (I - 1) * b_next
+        blend_ms = float(sweep_ms.sum(axis=1).mean())
+        traffic = profiled_traffic() if args.config == "c3" and world == 1 else None
+        # per-stage byte model of SURVEY.md 8d (per GPU): front end = 24 B/ray + 4 B per voxel (S_vox written) + the
+        # feature maps once; depth = 12 B per voxel + 4 B per ray; grid work = 3 x 4 B x G^3 per sweep
+        feat_bytes = len(my_views) * (H + PADDING + 1) * (W + PADDING + 1) * F * 4.0
+        fe_bytes = 24.0 * n_rays + 4.0 * sum_L + feat_bytes
+        de_bytes = 12.0 * sum_L + 4.0 * n_rays
+        grid_bytes = I * 3 * G ** 3 * 4.0
+        fe_ms, bp_ms, de_ms = (float(stages[:, k].mean()) for k in range(3))
+        step_bytes = fe_bytes + blend_bytes + de_bytes + grid_bytes
+
+        def frac(nbytes, ms):
+            return nbytes / (ms * 1e-3) / 1e9 / peak
+
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": cfg["label"], "rays_per_gpu": n_rays, "rays_total": total_rays,
-                "reference_images_per_gpu": len(my_images), "bp_sweeps": I, "max_voxels": M,
-                "mean_voxels_per_ray": mean_L, "longest_ray": max_L, "parallelism": "rays sharded, dp%d" % world,
+                "workload": cfg["label"], "rays_total": total_rays, "rays_on_rank0": n_rays,
+                "segments_on_rank0": [[int(i), int(a), int(b)] for (i, a, b) in segs], "bp_sweeps": I, "max_voxels": M,
+                "mean_voxels_per_ray": mean_L, "longest_ray": max_L,
+                "parallelism": "rays sharded in %d contiguous blocks of the (image, pixel) enumeration" % world
+                               if scaling == "strong" else "whole reference images per rank, dp%d" % world,
                 "collective": ("all-reduce f32[%d^3] per sweep (NCCL)" % G) if world > 1 else "none",
-                "l2": "per-step working set (%.1f GB of per-ray state) is far larger than L2; no flush needed"
-                      % (2 * n_rays * M * 4 / 1e9),
+                "l2": "per-step working set (%.1f GB of per-ray state on rank 0) is far larger than L2; no flush needed"
+                      % (3 * n_rays * M * 4 / 1e9),
             },
             "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic or {}).get("bp_kernel_dram_bytes_per_launch") if args.config == "c3" else None,
-                "kernel": "bp4_kernel (one BP sweep over all rays of this rank = one launch per ray-length class)",
-                "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": sweep_avg_ms,
-                "launches_timed": len(sweep_ms), "peak_source": peak_src,
-                "step_model": {"bytes_per_step_per_gpu": step_bytes,
-                               "frac_of_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+                "bound": "hbm", "achieved": a_next, "peak": peak, "unit": "GB/s", "frac": a_next / peak,
+                "traffic": (traffic or {}).get("bp_kernel_dram_bytes_per_launch"),
+                "traffic_source": ((traffic or {}).get("source", "profiles/roofline_traffic.json") +
+                                   " (ncu capture of this configuration; not measured by this run)") if traffic else None,
+                "kernel": "bp4_kernel<NCH, false>: one NON-FIRST BP sweep over all rays of this rank = one launch per "
+                          "ray-length class, timed with CUDA events around the launch set",
+                "algorithmic_bytes_per_launch": b_next, "launch_ms": next_ms,
+                "launches_timed": int(sweep_ms[:, 1:].size), "peak_source": peak_src,
+                "first_sweep": {"kernel": "bp4_kernel<NCH, true>", "algorithmic_bytes_per_launch": b_first,
+                                "launch_ms": first_ms, "achieved": a_first, "frac": a_first / peak},
+                "all_sweeps": {"algorithmic_bytes": blend_bytes, "ms": blend_ms, "frac": frac(blend_bytes, blend_ms)},
+                "stages": {
+                    "frontend": {"algorithmic_bytes": fe_bytes, "ms": fe_ms, "frac": frac(fe_bytes, fe_ms),
+                                 "note": "bound by L2 -> SM gather bandwidth, not HBM: every (ray, plane, view) sample "
+                                         "is its own 128-byte feature vector (DESIGN.md 4)"},
+                    "bp": {"algorithmic_bytes": blend_bytes + grid_bytes, "ms": bp_ms, "frac": frac(blend_bytes + grid_bytes, bp_ms)},
+                    "depth": {"algorithmic_bytes": de_bytes, "ms": de_ms, "frac": frac(de_bytes, de_ms)},
+                },
+                "step_model": {"bytes_per_step_per_gpu": step_bytes, "frac_of_peak": frac(step_bytes, ms_step)},
             },
-            "stages_ms": {"frontend": float(stages[:, 0].mean()), "bp": float(stages[:, 1].mean()),
-                          "depth": float(stages[:, 2].mean())},
+            "stages_ms": {"frontend": fe_ms, "bp": bp_ms, "depth": de_ms,
+                          "bp_first_sweep": first_ms, "bp_next_sweep": next_ms},
             "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
         }
         if cnn is not None:
@@ -485,6 +570,7 @@ def run_gpu_arm(args, cfg):
         if world == 1 and not args.no_cpu:
             from oracle import oracle as orc
             orc.build()
+            orc.set_threads(host_cores())
             sample = cpu_calibrated_sample(cfg, 4.0)
             rays, secs, passes = cpu_timed_passes(sample, 15.0)
             line["cpu_baseline"] = {
@@ -505,6 +591,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="strong: the fixed job sharded by rays over the GPUs (default); weak: fixed work per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs only)")
     args = ap.parse_args()

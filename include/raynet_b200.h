@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RN_ABI_VERSION 2
+#define RN_ABI_VERSION 3
 
 typedef enum RnStatus {
     RN_OK = 0,
@@ -163,7 +163,7 @@ int rn_mvcnn_voxel_depth(const RnParams *p, const int32_t *ray_idxs, const float
  * loop of RayNetForwardPass.forward_pass, forward_pass.py:593-748, which re-runs the
  * front end and bounces messages through host memory on every sweep).
  *
- * Per-ray state kept in HBM between sweeps (max_voxels <= 1024; R = rn_row_stride(max_voxels)):
+ * Per-ray state kept in HBM between sweeps (max_voxels <= 1536; R = rn_row_stride(max_voxels)):
  *   ray_hdr   uint32 [n][2]  first voxel + step signs      (8 B / ray)
  *   codes     uint8  [n][code_stride]  2 bits per traversed voxel, stored as one (lo, hi) pair
  *             of 32-bit bit planes per 32 voxels; code = the axis stepped along to ENTER the
@@ -193,12 +193,15 @@ int rn_bricks_to_grid(const RnParams *p, const float *bricks, float *grid, int a
  * view_ids (may be NULL): int32 [V], the slot inside `features` of each of the V views of
  * this reference image, so that one resident feature volume [n_feature_slots][H+p+1][W+p+1][F]
  * serves every reference image (the reference re-uploads a re-ordered copy per image,
- * forward_pass.py:622-641).  NULL means slots 0..V-1. */
+ * forward_pass.py:622-641).  NULL means slots 0..V-1.
+ * starts / ends: float32 [n][3] (required, written); plane_scratch: float32 [n][depth_planes],
+ * caller-owned scratch for the per-ray plane distribution (required when feat_dim == 32; the library
+ * keeps no hidden per-thread buffers, so calls on different streams never share state). */
 int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *features,
                        const int32_t *view_ids, int32_t n_feature_slots, const float *P,
                        const float *P_inv, const float *centre, const float *axis_centres, float *starts,
-                       float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *s_hat,
-                       int32_t *lin, int64_t n_rays, void *stream);
+                       float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *plane_scratch,
+                       float *s_hat, int32_t *lin, int64_t n_rays, void *stream);
 
 /* SURVEY.md 8(f) row 1 -- the MV-CNN feature extractor in front of the path (models.py:90-111,
  * forward_pass.py:181-198): one 'valid' 3x3 convolution to 32 channels with the inference-mode batch
@@ -246,8 +249,8 @@ int rn_engine_trace(const RnParams *p, const int32_t *ray_idxs, const float *P_i
                     void *stream);
 int rn_engine_similarity(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
                          const float *P, const float *axis_centres, const float *starts, const float *ends,
-                         const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count, float *s_hat,
-                         int32_t *lin, int64_t n_rays, void *stream);
+                         const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count, float *plane_scratch,
+                         float *s_hat, int32_t *lin, int64_t n_rays, void *stream);
 
 /* Group the rays by length class (class c = ceil(count / 128) for count >= 2, class 0 = the rays
  * BP skips) so that each class runs with the shared memory its rays need.  order: int32 [n]
@@ -295,6 +298,36 @@ int rn_add_prior(float *acc, float prior, int64_t n, void *stream);
 
 /* max over count[0:n] written to *out_max (device int32). */
 int rn_max_count(const int32_t *count, int64_t n, int32_t *out_max, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Parity mode -- float64 accumulators.  mrf_np.py as it executes under NumPy >= 2
+ * keeps both accumulators in float64 (mrf_np.py:285-292), which makes the occupancy-to-ray chain
+ * float64 while messages stay float32.  These entry points follow that flavour statement for
+ * statement (RED.ADD.F64 scatter-add; float64 o / cp / prefix / suffix; float32 pos, neg, p, log),
+ * so that I sweeps can be gated END TO END at 1e-5 against the reference.  Same buffers as their
+ * float32 twins except that the accumulators are float64; multi-GPU: all-reduce the float64 grid.
+ * ------------------------------------------------------------------------------------- */
+int rn_fill_f64(double *dst, double value, int64_t n, void *stream);
+int rn_occupancy_f64(const double *acc, float *out, int64_t n, void *stream);      /* mrf_np.py:206-240 */
+int rn_grid_to_bricks_f64(const RnParams *p, const double *grid, double *bricks, double pad, void *stream);
+/* bricks -> row-major float64 grid (may be NULL) and / or float32 sigmoid(acc) (may be NULL) */
+int rn_bricks_to_grid_f64(const RnParams *p, const double *bricks, double *grid, float *occupancy, void *stream);
+/* rn_bp_iteration / rn_depth_estimate on the reference's buffers (mrf_cuda.py:37-122), accumulators
+ * float64 row-major [Gx][Gy][Gz]; S is clipped / renormalised on the fly exactly as mrf_np.py:4-8. */
+int rn_bp_iteration_f64(const RnParams *p, const float *S, const int32_t *ray_voxel_indices,
+                        const int32_t *ray_voxel_count, const double *acc_in, float *msgs, double *acc_out,
+                        int64_t n_rays, void *stream);
+int rn_depth_estimate_f64(const RnParams *p, const float *S, const int32_t *ray_voxel_indices,
+                          const int32_t *ray_voxel_count, const double *acc, const float *msgs, float *S_new,
+                          int64_t n_rays, void *stream);
+/* rn_engine_bp_iteration / rn_engine_depth on the resident state, accumulators float64 bricked. */
+int rn_engine_bp_iteration_f64(const RnParams *p, const int32_t *lin, const int32_t *count, const float *s_hat,
+                               float *msgs, const double *acc_in, double *acc_out, int32_t first_sweep,
+                               int64_t n_rays, void *stream);
+int rn_engine_depth_f64(const RnParams *p, const int32_t *lin, const int32_t *count, const float *s_hat,
+                        const float *msgs, const double *acc, const float *axis_centres, const float *centres,
+                        const int64_t *seg_starts, int32_t n_seg, float *depth_map, float *S_new, int64_t n_rays,
+                        void *stream);
 
 #ifdef __cplusplus
 }

@@ -67,9 +67,9 @@ SIGNATURES = {
     "rn_raynet_de": [_PP] + [_PTR] * 12 + [_I64, _PTR],
     "rn_mvcnn_voxel": [_PP] + [_PTR] * 9 + [_I64, _PTR],
     "rn_mvcnn_voxel_depth": [_PP] + [_PTR] * 10 + [_I64, _PTR],
-    "rn_engine_frontend": [_PP, _PTR, _PTR, _PTR, _I32] + [_PTR] * 11 + [_I64, _PTR],
+    "rn_engine_frontend": [_PP, _PTR, _PTR, _PTR, _I32] + [_PTR] * 12 + [_I64, _PTR],
     "rn_engine_trace": [_PP] + [_PTR] * 8 + [_I64, _PTR],
-    "rn_engine_similarity": [_PP, _PTR, _PTR, _I32] + [_PTR] * 9 + [_I64, _PTR],
+    "rn_engine_similarity": [_PP, _PTR, _PTR, _I32] + [_PTR] * 10 + [_I64, _PTR],
     "rn_conv3x3_bn_relu": [_PTR] * 5 + [_I32] * 5 + [_PTR],
     "rn_fuse_depth_maps": [_PTR] * 6 + [_I32] * 5 + [_PTR, _PTR, _PTR],
     "rn_nn_grid_distances": [_PTR, _I64, _PTR, _PTR, _PTR, ctypes.c_float, _PTR, _I32, _PTR, _PTR],
@@ -82,6 +82,15 @@ SIGNATURES = {
     "rn_axis_centres": [_PP, _PTR, _PTR, _PTR],
     "rn_add_prior": [_PTR, ctypes.c_float, _I64, _PTR],
     "rn_max_count": [_PTR, _I64, _PTR, _PTR],
+    # parity mode (float64 accumulators)
+    "rn_fill_f64": [_PTR, ctypes.c_double, _I64, _PTR],
+    "rn_occupancy_f64": [_PTR, _PTR, _I64, _PTR],
+    "rn_grid_to_bricks_f64": [_PP, _PTR, _PTR, ctypes.c_double, _PTR],
+    "rn_bricks_to_grid_f64": [_PP, _PTR, _PTR, _PTR, _PTR],
+    "rn_bp_iteration_f64": [_PP, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _PTR],
+    "rn_depth_estimate_f64": [_PP, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _PTR],
+    "rn_engine_bp_iteration_f64": [_PP] + [_PTR] * 6 + [_I32, _I64, _PTR],
+    "rn_engine_depth_f64": [_PP] + [_PTR] * 8 + [_I32, _PTR, _PTR, _I64, _PTR],
 }
 OTHER_SYMBOLS = ["rn_last_error", "rn_abi_version", "rn_device_info", "rn_code_stride", "rn_row_stride", "rn_num_classes",
                  "rn_brick_elems"]

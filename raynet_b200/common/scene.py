@@ -105,8 +105,13 @@ class Scene(object):
     def get_images(self):
         return [self.get_image(i) for i in range(self.n_images)]
 
+    def view_order(self, i, neighbors=4):
+        """Scene indices of [reference, neighbours...] -- what get_image_with_neighbors(i) returns, as indices
+        (RayNetForwardPass keeps one feature map per distinct view)."""
+        return [int(i)] + [int(n) for n in self._get_neighbor_idxs(i, neighbors)]
+
     def get_image_with_neighbors(self, i, neighbors=4):
-        return [self.get_image(i)] + [self.get_image(int(n)) for n in self._get_neighbor_idxs(i, neighbors)]
+        return [self.get_image(j) for j in self.view_order(i, neighbors)]
 
     def voxel_grid(self, grid_shape):
         if self._voxel_grid is None:

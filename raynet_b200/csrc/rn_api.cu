@@ -6,8 +6,8 @@
 #include <cstdlib>
 
 #include "rn_kernels.cuh"
-#include "rn_bp3.cuh"
 #include "rn_bp4.cuh"
+#include "rn_parity.cuh"
 #include "rn_simmap3.cuh"
 #include "rn_cnn.cuh"
 #include "rn_fusion.cuh"
@@ -86,6 +86,47 @@ int make_dev(const RnParams *p, RnDev &d, bool need_grid, bool need_views, bool 
 
 inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Largest dynamic shared memory size a kernel has been opted into, PER DEVICE (the attribute is per
+// device; a process may drive several).  Races are benign: the worst case sets the attribute twice.
+struct SmemOptIn {
+    size_t configured[64] = {};
+    template <typename K>
+    int ensure(K kernel, size_t smem, const char *what) {
+        if (smem <= 48 * 1024) return RN_OK;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+        const int slot = dev & 63;
+        if (smem <= configured[slot]) return RN_OK;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "%s shared-memory opt-in (%zu bytes): %s", what, smem, cudaGetErrorString(e));
+        configured[slot] = smem;
+        return RN_OK;
+    }
+};
+
+// Scratch of the entry points that mirror a reference signature (no room for a caller-owned buffer):
+// allocated and freed IN STREAM ORDER on the caller's stream, so two streams never share a buffer,
+// the memory belongs to the current device and nothing is freed under a running kernel.
+int scratch_alloc(void **ptr, size_t bytes, cudaStream_t st) {
+    static bool pool_ready[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && !pool_ready[dev & 63]) {   // keep freed scratch in the pool instead of returning it to the driver
+        cudaMemPool_t pool;
+        e = cudaDeviceGetDefaultMemPool(&pool, dev);
+        uint64_t keep = ~0ull;
+        if (e == cudaSuccess) e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pool_ready[dev & 63] = (e == cudaSuccess);
+    }
+    if (e == cudaSuccess) e = cudaMallocAsync(ptr, bytes, st);
+    if (e != cudaSuccess) { *ptr = nullptr; return fail(RN_ERR_CUDA, "scratch allocation of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
+    return RN_OK;
+}
+void scratch_free(void *ptr, cudaStream_t st) {
+    if (ptr) cudaFreeAsync(ptr, st);
+}
+
 int launch_dda(const RnDev &d, const DdaArgs &a, cudaStream_t st) {
     if (a.n_rays <= 0) return RN_OK;
     const int threads = 128;
@@ -116,61 +157,50 @@ int launch_simmap(const RnDev &d, SimMapArgs a, bool mapping, cudaStream_t st) {
     if (!mapping) a.count = nullptr;
     a.val_stride = mapping ? (int)row_stride_of(d.M) : 0;
     a.tile_len = tile_len_for(d, a.n_rays);
-    { const char *m = getenv("RN_TILE_MODE"); a.tile_mode = m ? atoi(m) : 2; }
+    a.tile_mode = 2;
     const size_t smem = rn_simmap_smem_bytes(d.D, d.V, a.val_stride, warps);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(simmap_kernel<kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "simmap smem attribute: %s", cudaGetErrorString(e));
-        configured = smem;
-    }
+    static SmemOptIn opt;
+    if (int rc = opt.ensure(simmap_kernel<kAos>, smem, "simmap_kernel")) return rc;
     const int64_t blocks = (a.n_rays + warps - 1) / warps;
     simmap_kernel<kAos><<<(unsigned)blocks, warps * 32, smem, st>>>(d, a);
     return check_launch("simmap_kernel");
 }
 
-// Resident front end, F = 32 (rn_simmap3.cuh): similarity + softmax -> S_planes scratch, then
-// plane->voxel mapping -> s_hat, lin.
-struct PlaneScratch {
-    float *ptr = nullptr;
-    int64_t cap = 0;
-};
-thread_local PlaneScratch g_planes;
+// Resident front end, F = 32 (rn_simmap3.cuh): similarity + softmax -> S_planes scratch (caller-owned,
+// n_rays x depth_planes floats), then plane->voxel mapping -> s_hat, lin.
+inline size_t simscore3_smem(const RnDev &d) {
+    return sizeof(float) * (rn_simscore3_cta_words(d.V) + 4 * rn_simscore3_warp_words(d.D, d.V));
+}
 
-int launch_simmap3(const RnDev &d, SimMapArgs a, cudaStream_t st) {
+template <int VT>
+int launch_simscore3(const RnDev &d, const SimMapArgs &a, size_t smem, cudaStream_t st) {
+    static SmemOptIn opt;
+    if (int rc = opt.ensure(simscore3_kernel<VT>, smem, "simscore3_kernel")) return rc;
+    simscore3_kernel<VT><<<(unsigned)((a.n_rays + 3) / 4), 128, smem, st>>>(d, a);
+    return check_launch("simscore3_kernel");
+}
+
+int launch_simmap3(const RnDev &d, SimMapArgs a, float *plane_scratch, cudaStream_t st) {
     if (a.n_rays <= 0) return RN_OK;
-    const int64_t need = a.n_rays * (int64_t)d.D;
-    if (g_planes.cap < need) {
-        if (g_planes.ptr) cudaFree(g_planes.ptr);
-        cudaError_t e = cudaMalloc(&g_planes.ptr, sizeof(float) * (size_t)need);
-        if (e != cudaSuccess) { g_planes.ptr = nullptr; g_planes.cap = 0; return fail(RN_ERR_CUDA, "cudaMalloc plane scratch: %s", cudaGetErrorString(e)); }
-        g_planes.cap = need;
-    }
-    a.S_planes = g_planes.ptr;
+    a.S_planes = plane_scratch;
     a.val_stride = (int)row_stride_of(d.M);
     a.tile_len = tile_len_for(d, a.n_rays);
-    { const char *m = getenv("RN_TILE_MODE"); a.tile_mode = m ? atoi(m) : 2; }
-    const size_t smem_a = sizeof(float) * (rn_simscore3_cta_words(d.V) + 4 * rn_simscore3_warp_words(d.D, d.V));
+    a.tile_mode = 2;
+    const size_t smem_a = simscore3_smem(d);
     const size_t smem_b = sizeof(float) * (rn_planemap3_cta_words(d.gx + d.gy + d.gz) + 4 * rn_planemap3_warp_words(d.D, a.val_stride));
-    static thread_local size_t conf_b = 0;
-    if (smem_a > 48 * 1024) return fail(RN_ERR_UNSUPPORTED, "depth_planes x n_views too large for the similarity kernel's shared memory");
-    if (smem_b > 48 * 1024 && smem_b > conf_b) {
-        cudaError_t e = cudaFuncSetAttribute(planemap3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "planemap3 smem attribute: %s", cudaGetErrorString(e));
-        conf_b = smem_b;
-    }
-    const unsigned blocks_a = (unsigned)((a.n_rays + 3) / 4);
+    int rc;
     switch (d.V) {   // common view counts get fully unrolled loops
-        case 3: simscore3_kernel<3><<<blocks_a, 128, smem_a, st>>>(d, a); break;
-        case 5: simscore3_kernel<5><<<blocks_a, 128, smem_a, st>>>(d, a); break;
-        case 7: simscore3_kernel<7><<<blocks_a, 128, smem_a, st>>>(d, a); break;
-        case 9: simscore3_kernel<9><<<blocks_a, 128, smem_a, st>>>(d, a); break;
-        case 11: simscore3_kernel<11><<<blocks_a, 128, smem_a, st>>>(d, a); break;
-        case 15: simscore3_kernel<15><<<blocks_a, 128, smem_a, st>>>(d, a); break;
-        default: simscore3_kernel<0><<<blocks_a, 128, smem_a, st>>>(d, a); break;
+        case 3: rc = launch_simscore3<3>(d, a, smem_a, st); break;
+        case 5: rc = launch_simscore3<5>(d, a, smem_a, st); break;
+        case 7: rc = launch_simscore3<7>(d, a, smem_a, st); break;
+        case 9: rc = launch_simscore3<9>(d, a, smem_a, st); break;
+        case 11: rc = launch_simscore3<11>(d, a, smem_a, st); break;
+        case 15: rc = launch_simscore3<15>(d, a, smem_a, st); break;
+        default: rc = launch_simscore3<0>(d, a, smem_a, st); break;
     }
-    int rc = check_launch("simscore3_kernel");
     if (rc) return rc;
+    static SmemOptIn opt_b;
+    if ((rc = opt_b.ensure(planemap3_kernel, smem_b, "planemap3_kernel"))) return rc;
     const int64_t per_cta = 4 * RN_SM3_RAYS_PER_WARP;
     planemap3_kernel<<<(unsigned)((a.n_rays + per_cta - 1) / per_cta), 128, smem_b, st>>>(d, a);
     return check_launch("planemap3_kernel");
@@ -180,16 +210,12 @@ int launch_simmap3(const RnDev &d, SimMapArgs a, cudaStream_t st) {
 template <int CIN>
 int launch_conv3x3(const ConvArgs &a, cudaStream_t st) {
     const size_t smem = sizeof(float) * rn_cnn_smem_words<CIN>();
-    static thread_local bool configured = false;
-    static thread_local int sms = 0;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int dev = 0;
-        if (e == cudaSuccess) e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "conv3x3 setup: %s", cudaGetErrorString(e));
-        configured = true;
-    }
+    static SmemOptIn opt;
+    if (int rc = opt.ensure(conv3x3_kernel<CIN>, smem, "conv3x3_kernel")) return rc;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail(RN_ERR_CUDA, "conv3x3 setup: %s", cudaGetErrorString(e));
     const int ho = a.hi - 2, wo = a.wi - 2;
     const int64_t tiles = (int64_t)a.n * ((ho + RN_CNN_TH - 1) / RN_CNN_TH) * ((wo + RN_CNN_TW - 1) / RN_CNN_TW);
     const int64_t resident = (int64_t)sms * (smem > 100 * 1024 ? 1 : 2);   // persistent CTAs: one wave
@@ -203,50 +229,29 @@ int launch_bp2(const RnDev &d, Bp2Args a, bool first_sweep, int nch_max, cudaStr
     if (a.n <= 0) return RN_OK;
     if (nch_max < 1 || nch_max > RN_MAX_NCH)
         return fail(RN_ERR_UNSUPPORTED, "rays longer than %d voxels are not supported", RN_MAX_NCH * RN_CHUNK);
-    static thread_local bool configured = false;
-    if (!configured) {   // the largest class needs more than the 48 KB default
-        const int mx = (int)(4 * rn_bp2_warp_bytes(RN_MAX_NCH));
-        cudaError_t e = cudaFuncSetAttribute(bp2_kernel<true, kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bp2_kernel<false, kAos>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "bp2 smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
-    }
     a.nch_max = nch_max;
     const size_t smem = 4 * rn_bp2_warp_bytes(nch_max);
+    static SmemOptIn opt_first, opt_next;
+    int rc = first_sweep ? opt_first.ensure(bp2_kernel<true, kAos>, smem, "bp2_kernel")
+                         : opt_next.ensure(bp2_kernel<false, kAos>, smem, "bp2_kernel");
+    if (rc) return rc;
     const unsigned blocks = (unsigned)((a.n + 3) / 4);
     if (first_sweep) bp2_kernel<true, kAos><<<blocks, 128, smem, st>>>(d, a);
     else bp2_kernel<false, kAos><<<blocks, 128, smem, st>>>(d, a);
     return check_launch("bp2_kernel");
 }
 
-// Register-resident sweep for one length class (rays of exactly nch chunks), resident layout only.
-template <int NCH>
-int launch_bp3_n(const RnDev &d, const Bp2Args &a, bool first_sweep, cudaStream_t st) {
-    const unsigned blocks = (unsigned)((a.n + RN_BP3_RAYS_PER_CTA - 1) / RN_BP3_RAYS_PER_CTA);
-    if (a.debug & 8) {
-        bp_memonly_kernel<NCH><<<(unsigned)((a.n + 3) / 4), 128, 0, st>>>(d, a);
-        return check_launch("bp_memonly_kernel");
-    }
-    if (first_sweep) bp3_kernel<NCH, true><<<blocks, 128, 0, st>>>(d, a);
-    else bp3_kernel<NCH, false><<<blocks, 128, 0, st>>>(d, a);
-    return check_launch("bp3_kernel");
-}
-
-// Prefetching register-resident sweep (rn_bp4.cuh); every ray of the launch has exactly NCH chunks.
+// Register-resident sweep with TMA-staged rows (rn_bp4.cuh); every ray of the launch has exactly NCH chunks.
 template <int NCH, bool kFirst>
 int launch_bp4_nf(const RnDev &d, Bp2Args a, cudaStream_t st) {
-    const size_t smem = (size_t)4 * rn_bp4_warp_words(NCH, kFirst) * sizeof(float);
-    static thread_local bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(bp4_kernel<NCH, kFirst>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(RN_ERR_CUDA, "bp4 smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
-    }
-    static const int rpw = [] { const char *e = getenv("RN_BP4_RPW"); int v = e ? atoi(e) : RN_BP4_RAYS_PER_WARP; return v > 0 ? v : RN_BP4_RAYS_PER_WARP; }();
-    a.rays_per_warp = rpw;
-    const int per_cta = 4 * rpw;
+    constexpr int WARPS = rn_bp4_warps(NCH);
+    const size_t smem = (size_t)WARPS * rn_bp4_warp_words(NCH, kFirst) * sizeof(float);
+    static SmemOptIn opt;
+    if (int rc = opt.ensure(bp4_kernel<NCH, kFirst>, smem, "bp4_kernel")) return rc;
+    a.rays_per_warp = RN_BP4_RAYS_PER_WARP;
+    const int per_cta = WARPS * a.rays_per_warp;
     const unsigned blocks = (unsigned)((a.n + per_cta - 1) / per_cta);
-    bp4_kernel<NCH, kFirst><<<blocks, 128, smem, st>>>(d, a);
+    bp4_kernel<NCH, kFirst><<<blocks, 32 * WARPS, smem, st>>>(d, a);
     return check_launch("bp4_kernel");
 }
 template <int NCH>
@@ -254,12 +259,10 @@ int launch_bp4_n(const RnDev &d, const Bp2Args &a, bool first_sweep, cudaStream_
     return first_sweep ? launch_bp4_nf<NCH, true>(d, a, st) : launch_bp4_nf<NCH, false>(d, a, st);
 }
 
-#define RN_BP3_MAX_NCH 6
 // exact_class: every ray of the launch has exactly nch chunks (binned launches)
 int launch_bp_class(const RnDev &d, Bp2Args a, bool first_sweep, int nch, cudaStream_t st, bool exact_class) {
     if (a.n <= 0) return RN_OK;
-    static const int impl = [] { const char *e = getenv("RN_BP_IMPL"); return e ? atoi(e) : 4; }();
-    if (impl == 4 && exact_class && nch <= RN_BP3_MAX_NCH) {
+    if (exact_class) {
         switch (nch) {
             case 1: return launch_bp4_n<1>(d, a, first_sweep, st);
             case 2: return launch_bp4_n<2>(d, a, first_sweep, st);
@@ -267,21 +270,15 @@ int launch_bp_class(const RnDev &d, Bp2Args a, bool first_sweep, int nch, cudaSt
             case 4: return launch_bp4_n<4>(d, a, first_sweep, st);
             case 5: return launch_bp4_n<5>(d, a, first_sweep, st);
             case 6: return launch_bp4_n<6>(d, a, first_sweep, st);
+            case 7: return launch_bp4_n<7>(d, a, first_sweep, st);
+            case 8: return launch_bp4_n<8>(d, a, first_sweep, st);
+            case 9: return launch_bp4_n<9>(d, a, first_sweep, st);
+            case 10: return launch_bp4_n<10>(d, a, first_sweep, st);
+            case 11: return launch_bp4_n<11>(d, a, first_sweep, st);
+            case 12: return launch_bp4_n<12>(d, a, first_sweep, st);
         }
     }
-    static const int dbg = [] { const char *e = getenv("RN_BP_DEBUG"); return e ? atoi(e) : 0; }();
-    a.debug = dbg;
-    if (impl == 3 && nch <= RN_BP3_MAX_NCH) {
-        switch (nch) {
-            case 1: return launch_bp3_n<1>(d, a, first_sweep, st);
-            case 2: return launch_bp3_n<2>(d, a, first_sweep, st);
-            case 3: return launch_bp3_n<3>(d, a, first_sweep, st);
-            case 4: return launch_bp3_n<4>(d, a, first_sweep, st);
-            case 5: return launch_bp3_n<5>(d, a, first_sweep, st);
-            case 6: return launch_bp3_n<6>(d, a, first_sweep, st);
-        }
-    }
-    return launch_bp2<false>(d, a, first_sweep, nch, st);
+    return launch_bp2<false>(d, a, first_sweep, nch, st);   // unbinned rays: one launch sized for the longest
 }
 
 template <bool kAos>
@@ -298,44 +295,13 @@ inline unsigned grid_for(int64_t n, int threads, int64_t cap = 148 * 16) {
     return (unsigned)b;
 }
 
-// Per-stream scratch for the axis-centre table used by the reference-layout entry points
-// (they receive the full voxel_grid table like the reference does).
-struct AxisScratch {
-    float *ptr = nullptr;
-    int cap = 0;
-};
-thread_local AxisScratch g_axes;
-
-// Scratch for the ray start / end points handed from the DDA kernel to the similarity kernel
-// when the caller does not ask for them.
-struct RayScratch {
-    float *ptr = nullptr;
-    int64_t cap = 0;
-};
-thread_local RayScratch g_rays;
-
-int ray_scratch(int64_t n_rays, float **starts, float **ends) {
-    if (g_rays.cap < n_rays) {
-        if (g_rays.ptr) cudaFree(g_rays.ptr);
-        cudaError_t e = cudaMalloc(&g_rays.ptr, sizeof(float) * 6 * (size_t)n_rays);
-        if (e != cudaSuccess) { g_rays.ptr = nullptr; g_rays.cap = 0; return fail(RN_ERR_CUDA, "cudaMalloc ray scratch: %s", cudaGetErrorString(e)); }
-        g_rays.cap = n_rays;
-    }
-    *starts = g_rays.ptr;
-    *ends = g_rays.ptr + 3 * n_rays;
-    return RN_OK;
-}
-
+// The reference-layout entry points receive the full voxel_grid table like the reference does; its three
+// axis slices are extracted into stream-ordered scratch (scratch_alloc above).
 int axes_from_voxel_grid(const RnDev &d, const float *voxel_grid, float **axes, cudaStream_t st) {
     const int n = d.gx + d.gy + d.gz;
-    if (g_axes.cap < n) {
-        if (g_axes.ptr) cudaFree(g_axes.ptr);
-        cudaError_t e = cudaMalloc(&g_axes.ptr, sizeof(float) * (size_t)n);
-        if (e != cudaSuccess) { g_axes.ptr = nullptr; g_axes.cap = 0; return fail(RN_ERR_CUDA, "cudaMalloc axes: %s", cudaGetErrorString(e)); }
-        g_axes.cap = n;
-    }
-    axis_centres_kernel<<<(n + 127) / 128, 128, 0, st>>>(d, voxel_grid, g_axes.ptr);
-    *axes = g_axes.ptr;
+    int rc = scratch_alloc(reinterpret_cast<void **>(axes), sizeof(float) * (size_t)n, st);
+    if (rc) return rc;
+    axis_centres_kernel<<<(n + 127) / 128, 128, 0, st>>>(d, voxel_grid, *axes);
     return check_launch("axis_centres_kernel");
 }
 
@@ -452,7 +418,9 @@ int rn_planes_to_voxels(const RnParams *p, const float *voxel_grid, const int32_
     rc = axes_from_voxel_grid(d, voxel_grid, &axes, S(stream));
     if (rc) return rc;
     planes_to_voxels_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, S(stream)>>>(d, axes, ray_voxel_indices, ray_voxel_count, starts, ends, S_in, S_new, n_rays);
-    return check_launch("planes_to_voxels");
+    rc = check_launch("planes_to_voxels");
+    scratch_free(axes, S(stream));
+    return rc;
 }
 
 int rn_bp_iteration(const RnParams *p, const float *S_in, const int32_t *ray_voxel_indices,
@@ -548,13 +516,24 @@ int rn_max_count(const int32_t *count, int64_t n, int32_t *out_max, void *stream
 }
 
 // ---- fused reference-layout entry points ----------------------------------------------------
-static int frontend_ref_layout(const RnDev &d, const int32_t *ray_idxs, const float *features, const float *P,
-                               const float *P_inv, const float *centre, const float *axes,
+// Front end into the reference's buffers.  Scratch (axis-centre table, ray start / end) is allocated in
+// stream order and handed back to the caller to free after its own kernels.
+struct RefScratch {
+    float *axes = nullptr, *rays = nullptr;
+    cudaStream_t st = nullptr;
+    ~RefScratch() { scratch_free(axes, st); scratch_free(rays, st); }
+};
+
+static int frontend_ref_layout(const RnDev &d, RefScratch &sc, const int32_t *ray_idxs, const float *features,
+                               const float *P, const float *P_inv, const float *centre, const float *voxel_grid,
                                int32_t *ray_voxel_indices, int32_t *ray_voxel_count, float *S_vox,
                                float *depth_vox, int64_t n_rays, cudaStream_t st) {
-    float *starts = nullptr, *ends = nullptr;
-    int rc = ray_scratch(n_rays, &starts, &ends);
+    sc.st = st;
+    int rc = axes_from_voxel_grid(d, voxel_grid, &sc.axes, st);
     if (rc) return rc;
+    rc = scratch_alloc(reinterpret_cast<void **>(&sc.rays), sizeof(float) * 6 * (size_t)n_rays, st);
+    if (rc) return rc;
+    float *starts = sc.rays, *ends = sc.rays + 3 * n_rays;
     DdaArgs da = {};
     da.ray_idxs = ray_idxs; da.P_inv = P_inv; da.centre = centre; da.starts = starts; da.ends = ends;
     da.idx = ray_voxel_indices; da.count = ray_voxel_count; da.n_rays = n_rays;
@@ -563,7 +542,7 @@ static int frontend_ref_layout(const RnDev &d, const int32_t *ray_idxs, const fl
     SimMapArgs a = {};
     a.starts_in = starts; a.ends_in = ends;
     a.ray_idxs = ray_idxs; a.features = features; a.P = P; a.P_inv = P_inv; a.centre = centre;
-    a.axes = axes; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.S_vox = S_vox; a.depth_vox = depth_vox;
+    a.axes = sc.axes; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.S_vox = S_vox; a.depth_vox = depth_vox;
     a.n_rays = n_rays;
     return launch_simmap<true>(d, a, true, st);
 }
@@ -576,10 +555,8 @@ int rn_raynet_fp(const RnParams *p, const int32_t *ray_idxs, const float *featur
     int rc = make_dev(p, d, true, true, false);
     if (rc) return rc;
     if (n_rays <= 0) return RN_OK;
-    float *axes = nullptr;
-    rc = axes_from_voxel_grid(d, voxel_grid, &axes, S(stream));
-    if (rc) return rc;
-    rc = frontend_ref_layout(d, ray_idxs, features, P, P_inv, centre, axes, ray_voxel_indices, ray_voxel_count,
+    RefScratch sc;
+    rc = frontend_ref_layout(d, sc, ray_idxs, features, P, P_inv, centre, voxel_grid, ray_voxel_indices, ray_voxel_count,
                              S_voxel_space, nullptr, n_rays, S(stream));
     if (rc) return rc;
     Bp2Args a = {};
@@ -596,15 +573,13 @@ int rn_raynet_de(const RnParams *p, const int32_t *ray_idxs, const float *featur
     int rc = make_dev(p, d, true, true, false);
     if (rc) return rc;
     if (n_rays <= 0) return RN_OK;
-    float *axes = nullptr;
-    rc = axes_from_voxel_grid(d, voxel_grid, &axes, S(stream));
-    if (rc) return rc;
-    rc = frontend_ref_layout(d, ray_idxs, features, P, P_inv, centre, axes, ray_voxel_indices, ray_voxel_count,
+    RefScratch sc;
+    rc = frontend_ref_layout(d, sc, ray_idxs, features, P, P_inv, centre, voxel_grid, ray_voxel_indices, ray_voxel_count,
                              S_voxel_space, nullptr, n_rays, S(stream));
     if (rc) return rc;
     Depth2Args a = {};
     a.s_hat = S_voxel_space; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc = acc; a.msgs = msgs;
-    a.axes = axes; a.centres = centre; a.n_seg = 1; a.S_new = S_voxel_space; a.depth_map = depth_map; a.n_rays = n_rays;
+    a.axes = sc.axes; a.centres = centre; a.n_seg = 1; a.S_new = S_voxel_space; a.depth_map = depth_map; a.n_rays = n_rays;
     return launch_depth2<true>(d, a, S(stream));
 }
 
@@ -616,10 +591,8 @@ int rn_mvcnn_voxel(const RnParams *p, const int32_t *ray_idxs, const float *feat
     int rc = make_dev(p, d, true, true, false);
     if (rc) return rc;
     if (n_rays <= 0) return RN_OK;
-    float *axes = nullptr;
-    rc = axes_from_voxel_grid(d, voxel_grid, &axes, S(stream));
-    if (rc) return rc;
-    return frontend_ref_layout(d, ray_idxs, features, P, P_inv, centre, axes, ray_voxel_indices, ray_voxel_count,
+    RefScratch sc;
+    return frontend_ref_layout(d, sc, ray_idxs, features, P, P_inv, centre, voxel_grid, ray_voxel_indices, ray_voxel_count,
                                S_new, nullptr, n_rays, S(stream));
 }
 
@@ -631,10 +604,8 @@ int rn_mvcnn_voxel_depth(const RnParams *p, const int32_t *ray_idxs, const float
     int rc = make_dev(p, d, true, true, false);
     if (rc) return rc;
     if (n_rays <= 0) return RN_OK;
-    float *axes = nullptr;
-    rc = axes_from_voxel_grid(d, voxel_grid, &axes, S(stream));
-    if (rc) return rc;
-    return frontend_ref_layout(d, ray_idxs, features, P, P_inv, centre, axes, ray_voxel_indices, ray_voxel_count,
+    RefScratch sc;
+    return frontend_ref_layout(d, sc, ray_idxs, features, P, P_inv, centre, voxel_grid, ray_voxel_indices, ray_voxel_count,
                                S_new, depth_map, n_rays, S(stream));
 }
 
@@ -681,8 +652,8 @@ int rn_engine_trace(const RnParams *p, const int32_t *ray_idxs, const float *P_i
 
 int rn_engine_similarity(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
                          const float *P, const float *axis_centres, const float *starts, const float *ends,
-                         const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count, float *s_hat,
-                         int32_t *lin, int64_t n_rays, void *stream) {
+                         const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count, float *plane_scratch,
+                         float *s_hat, int32_t *lin, int64_t n_rays, void *stream) {
     RnDev d;
     int rc = make_dev(p, d, true, true, true);
     if (rc) return rc;
@@ -698,31 +669,30 @@ int rn_engine_similarity(const RnParams *p, const float *features, const int32_t
     a.features = features; a.view_ids = view_ids; a.P = P;
     a.axes = axis_centres; a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.lin = lin;
     a.n_rays = n_rays;
-    static const int impl = [] { const char *e = getenv("RN_SIMMAP_IMPL"); return e ? atoi(e) : 3; }();
-    // simscore3 addresses the feature volume with 32-bit BYTE offsets: below 4 GiB only
+    // the F = 32 kernels address the feature volume with 32-bit BYTE offsets (below 4 GiB only) and keep
+    // depth_planes x n_views offsets per warp in shared memory; anything else takes the generic kernel
     const int64_t feat_elems = (int64_t)(view_ids ? n_feature_slots : d.V) * d.fh * d.fw * d.F;
-    if (impl == 3 && d.F == 32 && feat_elems < (1ll << 30)) return launch_simmap3(d, a, S(stream));
+    if (d.F == 32 && feat_elems < (1ll << 30) && simscore3_smem(d) <= 200 * 1024) {
+        if (!plane_scratch) return fail(RN_ERR_SHAPE, "rn_engine_similarity needs plane_scratch (n_rays x depth_planes floats)");
+        return launch_simmap3(d, a, plane_scratch, S(stream));
+    }
     return launch_simmap<false>(d, a, true, S(stream));
 }
 
 int rn_engine_frontend(const RnParams *p, const int32_t *ray_idxs, const float *features,
                        const int32_t *view_ids, int32_t n_feature_slots, const float *P,
                        const float *P_inv, const float *centre, const float *axis_centres, float *starts,
-                       float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *s_hat,
-                       int32_t *lin, int64_t n_rays, void *stream) {
+                       float *ends, uint32_t *ray_hdr, uint8_t *codes, int32_t *count, float *plane_scratch,
+                       float *s_hat, int32_t *lin, int64_t n_rays, void *stream) {
     if (n_rays <= 0) {
         RnDev d;
         return make_dev(p, d, true, true, true);
     }
-    if ((starts == nullptr) != (ends == nullptr)) return fail(RN_ERR_SHAPE, "starts and ends must both be given or both NULL");
-    if (!starts) {
-        int rc = ray_scratch(n_rays, &starts, &ends);
-        if (rc) return rc;
-    }
+    if (!starts || !ends) return fail(RN_ERR_SHAPE, "rn_engine_frontend needs starts and ends buffers (n_rays x 3 floats each)");
     int rc = rn_engine_trace(p, ray_idxs, P_inv, centre, starts, ends, ray_hdr, codes, count, n_rays, stream);
     if (rc) return rc;
     return rn_engine_similarity(p, features, view_ids, n_feature_slots, P, axis_centres, starts, ends, ray_hdr, codes,
-                                count, s_hat, lin, n_rays, stream);
+                                count, plane_scratch, s_hat, lin, n_rays, stream);
 }
 
 int rn_engine_bin_rays(const RnParams *p, const int32_t *count, int64_t n_rays, int64_t seg_len, int32_t *order,
@@ -788,8 +758,7 @@ int rn_engine_depth(const RnParams *p, const int32_t *lin, const int32_t *count,
     a.lin = lin; a.count = count; a.s_hat = s_hat; a.msgs = msgs; a.acc = acc;
     a.axes = axis_centres; a.centres = centres; a.seg_starts = (n_seg > 1) ? seg_starts : nullptr; a.n_seg = n_seg;
     a.depth_map = depth_map; a.S_new = S_new; a.n_rays = n_rays;
-    static const int impl = [] { const char *e = getenv("RN_DEPTH_IMPL"); return e ? atoi(e) : 3; }();
-    if (impl == 3 && !S_new && depth_map && n_rays > 0) {   // resident fast path (rn_bp4.cuh)
+    if (!S_new && depth_map && n_rays > 0) {   // resident fast path (rn_bp4.cuh)
         depth3_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, S(stream)>>>(d, a);
         return check_launch("depth3_kernel");
     }
@@ -804,6 +773,96 @@ int rn_engine_expand_indices(const RnParams *p, const uint32_t *ray_hdr, const u
     if (n_rays <= 0) return RN_OK;
     expand_indices_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, S(stream)>>>(d, ray_hdr, codes, count, ray_voxel_indices, n_rays);
     return check_launch("expand_indices_kernel");
+}
+
+// ---- parity mode (rn_parity.cuh): float64 accumulators, the arithmetic of mrf_np.py under NumPy >= 2 ----
+int rn_fill_f64(double *dst, double value, int64_t n, void *stream) {
+    if (n <= 0) return RN_OK;
+    fill_f64_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(dst, value, n);
+    return check_launch("fill_f64_kernel");
+}
+
+int rn_occupancy_f64(const double *acc, float *out, int64_t n, void *stream) {
+    if (n <= 0) return RN_OK;
+    occupancy_f64_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(acc, out, n);
+    return check_launch("occupancy_f64_kernel");
+}
+
+int rn_grid_to_bricks_f64(const RnParams *p, const double *grid, double *bricks, double pad, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    const int64_t nb = (int64_t)d.bbx * d.bsx;
+    grid_to_bricks_f64_kernel<<<grid_for(nb, 256), 256, 0, S(stream)>>>(d, grid, bricks, pad, nb);
+    return check_launch("grid_to_bricks_f64_kernel");
+}
+
+int rn_bricks_to_grid_f64(const RnParams *p, const double *bricks, double *grid, float *occupancy, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    const int64_t n = (int64_t)d.gx * d.gy * d.gz;
+    bricks_to_grid_f64_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(d, bricks, grid, occupancy, n);
+    return check_launch("bricks_to_grid_f64_kernel");
+}
+
+int rn_bp_iteration_f64(const RnParams *p, const float *S_in, const int32_t *ray_voxel_indices,
+                        const int32_t *ray_voxel_count, const double *acc_in, float *msgs, double *acc_out,
+                        int64_t n_rays, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    if (n_rays <= 0) return RN_OK;
+    ParityArgs a = {};
+    a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.s = S_in; a.msgs = msgs; a.acc_in = acc_in; a.acc_out = acc_out;
+    a.n_rays = n_rays;
+    bp_parity_kernel<true><<<(unsigned)((n_rays + 3) / 4), 128, 0, S(stream)>>>(d, a);
+    return check_launch("bp_parity_kernel");
+}
+
+int rn_depth_estimate_f64(const RnParams *p, const float *S_in, const int32_t *ray_voxel_indices,
+                          const int32_t *ray_voxel_count, const double *acc, const float *msgs, float *S_new,
+                          int64_t n_rays, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    if (n_rays <= 0) return RN_OK;
+    ParityArgs a = {};
+    a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.s = S_in; a.msgs = const_cast<float *>(msgs); a.acc_in = acc;
+    a.S_new = S_new; a.n_rays = n_rays;
+    depth_parity_kernel<true><<<(unsigned)((n_rays + 3) / 4), 128, 0, S(stream)>>>(d, a);
+    return check_launch("depth_parity_kernel");
+}
+
+int rn_engine_bp_iteration_f64(const RnParams *p, const int32_t *lin, const int32_t *count, const float *s_hat,
+                               float *msgs, const double *acc_in, double *acc_out, int32_t first_sweep,
+                               int64_t n_rays, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, true);
+    if (rc) return rc;
+    if (n_rays <= 0) return RN_OK;
+    ParityArgs a = {};
+    a.lin = lin; a.count = count; a.s = s_hat; a.msgs = msgs; a.acc_in = acc_in; a.acc_out = acc_out;
+    a.first_sweep = first_sweep; a.n_rays = n_rays;
+    bp_parity_kernel<false><<<(unsigned)((n_rays + 3) / 4), 128, 0, S(stream)>>>(d, a);
+    return check_launch("bp_parity_kernel");
+}
+
+int rn_engine_depth_f64(const RnParams *p, const int32_t *lin, const int32_t *count, const float *s_hat,
+                        const float *msgs, const double *acc, const float *axis_centres, const float *centres,
+                        const int64_t *seg_starts, int32_t n_seg, float *depth_map, float *S_new, int64_t n_rays,
+                        void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, true);
+    if (rc) return rc;
+    if (n_seg < 1) return fail(RN_ERR_SHAPE, "n_seg must be at least 1");
+    if (n_rays <= 0) return RN_OK;
+    ParityArgs a = {};
+    a.lin = lin; a.count = count; a.s = s_hat; a.msgs = const_cast<float *>(msgs); a.acc_in = acc;
+    a.axes = axis_centres; a.centres = centres; a.seg_starts = (n_seg > 1) ? seg_starts : nullptr; a.n_seg = n_seg;
+    a.depth_map = depth_map; a.S_new = S_new; a.n_rays = n_rays;
+    depth_parity_kernel<false><<<(unsigned)((n_rays + 3) / 4), 128, 0, S(stream)>>>(d, a);
+    return check_launch("depth_parity_kernel");
 }
 
 }  // extern "C"

@@ -1,77 +1,136 @@
-// rn_bp4.cuh -- one BP sweep (a5 + a6): register-resident rays (rn_bp3.cuh) + software prefetch.
+// rn_bp4.cuh -- one BP sweep (a5 + a6) on the resident layout: register-resident rays, rows staged by TMA.
 //
-// Measurements behind this version (B200, C3, non-first sweep; profiles/README.md):
-//   * the memory operations of a sweep alone (bp_memonly_kernel: row reads, gathers, message
-//     stores, REDs, no arithmetic) take 3.55 ms; rows only 2.36 ms; the REDs cost 1.0 ms and the
-//     gathers 0.26 ms on top of the rows;
-//   * bp3_kernel (same memory operations + arithmetic) takes 4.7 ms: with ~100 registers per
-//     thread only 16-20 warps fit on an SM and each of them alternates between "load the whole
-//     ray" and "compute", so a good part of the load latency is exposed.
-// Here every warp works through a run of consecutive rays and the rows of the NEXT ray travel to
-// shared memory with cp.async (16 bytes per lane, L2 evict-first, no L1 allocation, no registers)
-// while the current ray is computed; the message buffer doubles as the transposition scratch
-// between the lane-consecutive gather / RED layout and the 4-voxels-per-lane scan layout.
+// History of this kernel (numbers: B200, C3, ms per non-first sweep; profiles/README.md):
+//   bp2_kernel  rows staged by TMA bulk copies, per-voxel state in shared memory        5.25
+//   (bp3)       state in registers per length class, rows loaded straight to registers  4.70
+//   bp4 round 1 bp3 + the NEXT ray's rows prefetched into shared memory by cp.async     3.73
+// ncu on the round-1 version: L1TEX data pipe 75 % busy, 3 * NCH LDGSTS per lane per ray for the row
+// staging on top of the gathers, the REDs and the transposition traffic.  This version stages the rows
+// with ONE elected lane issuing three cp.async.bulk copies per ray (TMA, UBLKCP: no LSU / L1TEX
+// involvement, completion on an mbarrier), keeps the transposition between the lane-consecutive gather /
+// RED layout and the 4-voxels-per-lane scan layout in a scratch of its own (no generic store ever
+// touches bytes the async proxy writes), and is instantiated for every length class up to
+// RN_MAX_NCH = 12 chunks (1536 voxels: C5), with CTAs of two warps for the long classes so that the
+// double-buffered rows of a CTA still allow several CTAs per SM.
 //
-// Contract: every ray of the launch has exactly NCH chunks (rn_class_of(L) == NCH, guaranteed by
-// the binning) -- only the last chunk is masked.
+// Rays are binned by length class (rn_class_of: NCH = ceil(L / 128) chunks); the kernel is instantiated
+// per class and fully unrolled: every per-voxel quantity that has to survive from the forward to the
+// backward pass (w_i, cp_i s_i, prefix sums) lives in registers.
+// Contract: every ray of the launch has exactly NCH chunks (guaranteed by the binning) -- only the
+// last chunk is masked.
 #pragma once
 
-#include "rn_bp3.cuh"
+#include "rn_engine.cuh"
 
-#ifndef RN_POL_ROWS
-#define RN_POL_ROWS 1     // evict-first hint on the prefetched rows
+__device__ __forceinline__ int rn_ld_stream_s32(const int32_t *p, uint64_t pol) {
+    int v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float4 rn_ld_stream4_pol(const float *p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void rn_st_stream4_pol(float *p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+}
+
+// min(o, 1 - o) = 1 / (1 + e^{|x|}) for o = sigmoid(x), clipped at 1e-4 (mrf_np.py:52-71); signed
+// like rn_occ_w.  e^{|x|} may overflow to +inf: rcp(inf) = 0 -> clipped to 1e-4, as intended.
+__device__ __forceinline__ float rn_occ_w2(float acc, float msg) {
+    const float x = acc - msg;
+    const float u = fmaxf(rn_rcp(1.0f + rn_ex2(fabsf(x) * 1.4426950408889634f)), 1e-4f);
+    return (x >= 0.f) ? -u : u;
+}
+
+#ifndef RN_BP4_RAYS_PER_WARP
+#define RN_BP4_RAYS_PER_WARP 8
 #endif
+#ifndef RN_BP4_TMA
+#define RN_BP4_TMA 1      // 1: rows staged by cp.async.bulk + mbarrier (TMA); 0: by per-lane 16-byte cp.async (LDGSTS)
+#endif
+
 __device__ __forceinline__ void rn_cp_async16(uint32_t dst_smem, const void *src, uint64_t pol) {
-    if (RN_POL_ROWS) asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(pol) : "memory");
-    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void rn_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void rn_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-#ifndef RN_BP4_RAYS_PER_WARP
-#define RN_BP4_RAYS_PER_WARP 8
-#endif
-
-// shared memory of one warp: 2 x (lin, s_hat) + (kFirst ? 1 : 2) x msgs rows of NCH * 128 words
-__host__ __device__ constexpr int rn_bp4_warp_words(int nch, bool first) { return nch * RN_CHUNK * (first ? 5 : 6); }
+// warps per CTA of a length class: the double-buffered rows of one warp take 24 * NCH * 128 bytes
+__host__ __device__ constexpr int rn_bp4_warps(int nch) { return nch <= 6 ? 4 : 2; }
+// shared memory words of one warp: 2 x (lin, s_hat) [+ 2 x msgs unless first sweep] rows of NCH * 128
+// words + 128 words of transposition scratch
+__host__ __device__ constexpr int rn_bp4_warp_words(int nch, bool first) { return nch * RN_CHUNK * (first ? 4 : 6) + RN_CHUNK; }
 
 template <int NCH, bool kFirst>
-__global__ void __launch_bounds__(128) bp4_kernel(RnDev p, Bp2Args a) {
-    extern __shared__ __align__(16) unsigned char rn_bp4_smem[];
+__global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp2Args a) {
+    extern __shared__ __align__(128) unsigned char rn_bp4_smem[];
     constexpr int ROW = NCH * RN_CHUNK;
+    constexpr int WARPS = rn_bp4_warps(NCH);
+    constexpr bool kTma = RN_BP4_TMA != 0;
+    __shared__ __align__(8) uint64_t bars[WARPS][2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float *base = reinterpret_cast<float *>(rn_bp4_smem) + (size_t)wid * rn_bp4_warp_words(NCH, kFirst);
-    // layout: lin[2][ROW], s_hat[2][ROW], msgs[kFirst ? 1 : 2][ROW]
+    // layout: lin[2][ROW], s_hat[2][ROW], (msgs[2][ROW],) scratch[128]
+    float *sX = base + (kFirst ? 4 : 6) * ROW;
     const uint64_t pol_stream = rn_policy_evict_first();
     const uint64_t pol_keep = rn_policy_evict_last();
 
-    // this warp's rays: positions k0 + 4 * t of the launch (the four warps of the CTA hold four
-    // consecutive entries of order[], i.e. neighbouring pixels, at any time)
+    if (kTma) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) {
+                rn_mbar_init(rn_smem_u32(&bars[w][0]), 1);
+                rn_mbar_init(rn_smem_u32(&bars[w][1]), 1);
+            }
+            rn_mbar_init_fence();
+        }
+        __syncthreads();
+    }
+
+    // this warp's rays: positions k0 + WARPS * t of the launch (the warps of the CTA hold consecutive
+    // entries of order[], i.e. neighbouring pixels, at any time)
     const int rpw = a.rays_per_warp;
-    const int64_t k0 = (int64_t)blockIdx.x * (4 * rpw) + wid;
+    const int64_t k0 = (int64_t)blockIdx.x * (WARPS * rpw) + wid;
     int nmine = 0;
-    if (k0 < a.n) nmine = (int)min((int64_t)rpw, (a.n - k0 + 3) / 4);
+    if (k0 < a.n) nmine = (int)min((int64_t)rpw, (a.n - k0 + WARPS - 1) / WARPS);
     if (nmine == 0) return;
 
     auto ray_of = [&](int t) -> int64_t {
-        const int64_t k = k0 + 4 * (int64_t)t;
+        const int64_t k = k0 + WARPS * (int64_t)t;
         return a.order ? (int64_t)__ldg(a.order + a.first + k) : a.first + k;
     };
     auto prefetch = [&](int64_t r, int L, int b) {
         const int32_t *lin_row = a.lin + r * (int64_t)p.row_stride;
         const float *s_row = a.s_hat + r * (int64_t)p.row_stride;
         const float *m_row = a.msgs + r * (int64_t)p.row_stride;
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const int i0 = c * RN_CHUNK + 4 * lane;
-            if (c < NCH - 1 || i0 < L) {
-                rn_cp_async16(rn_smem_u32(base + b * ROW + i0), lin_row + i0, pol_stream);
-                rn_cp_async16(rn_smem_u32(base + (2 + b) * ROW + i0), s_row + i0, pol_stream);
-                if (!kFirst) rn_cp_async16(rn_smem_u32(base + (4 + b) * ROW + i0), m_row + i0, pol_stream);
+        if (kTma) {
+            if (lane == 0) {   // rows hold whole quads: 16-byte multiples from 512-byte aligned rows
+                const uint32_t bytes = (uint32_t)((L + 3) & ~3) * 4u;
+                const uint32_t bar = rn_smem_u32(&bars[wid][b]);
+                rn_mbar_expect_tx(bar, bytes * (kFirst ? 2u : 3u));
+                rn_bulk_g2s(rn_smem_u32(base + b * ROW), lin_row, bytes, bar, pol_stream);
+                rn_bulk_g2s(rn_smem_u32(base + (2 + b) * ROW), s_row, bytes, bar, pol_stream);
+                if (!kFirst) rn_bulk_g2s(rn_smem_u32(base + (4 + b) * ROW), m_row, bytes, bar, pol_stream);
             }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int i0 = c * RN_CHUNK + 4 * lane;
+                if (c < NCH - 1 || i0 < L) {
+                    rn_cp_async16(rn_smem_u32(base + b * ROW + i0), lin_row + i0, pol_stream);
+                    rn_cp_async16(rn_smem_u32(base + (2 + b) * ROW + i0), s_row + i0, pol_stream);
+                    if (!kFirst) rn_cp_async16(rn_smem_u32(base + (4 + b) * ROW + i0), m_row + i0, pol_stream);
+                }
+            }
+            rn_cp_async_commit();
         }
-        rn_cp_async_commit();
     };
 
     int64_t r_cur = ray_of(0);
@@ -90,14 +149,15 @@ __global__ void __launch_bounds__(128) bp4_kernel(RnDev p, Bp2Args a) {
             prefetch(r_nxt, L_nxt, b ^ 1);
             r_cur = r_nxt; L_cur = L_nxt;
             if (t + 2 < nmine) { r_nxt = ray_of(t + 2); L_nxt = __ldg(a.count + r_nxt); }
-            rn_cp_async_wait<1>();
-        } else {
+            if (!kTma) rn_cp_async_wait<1>();
+        } else if (!kTma) {
             rn_cp_async_wait<0>();
         }
-        __syncwarp();   // ... and every lane's copies of ray t have landed
+        if (kTma) rn_mbar_wait(rn_smem_u32(&bars[wid][b]), (uint32_t)((t >> 1) & 1));   // buffer b: use number t / 2
+        else __syncwarp();   // ... and every lane's copies of ray t have landed
         const int *sLin = reinterpret_cast<const int *>(base + b * ROW);
         const float *sS = base + (2 + b) * ROW;
-        float *sM = base + (4 + (kFirst ? 0 : b)) * ROW;
+        const float *sM = base + (4 + b) * ROW;   // !kFirst only
         float *m_row = a.msgs + r * (int64_t)p.row_stride;
 
         // ---- accumulator gathers, lane-consecutive (neighbouring lanes share sectors) -------------
@@ -131,12 +191,18 @@ __global__ void __launch_bounds__(128) bp4_kernel(RnDev p, Bp2Args a) {
             const float4 s4 = *reinterpret_cast<const float4 *>(sS + i0);
             float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);   // first sweep: messages are 0 (mrf_np.py:275)
             if (!kFirst) m4 = *reinterpret_cast<const float4 *>(sM + i0);
-            __syncwarp();
+            float accv[4];
+            if (uniform) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) sM[c * RN_CHUNK + 32 * j + lane] = ga[c][j];
-            __syncwarp();
-            const float4 acc4 = *reinterpret_cast<const float4 *>(sM + i0);
-            const float accv[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+                for (int j = 0; j < 4; j++) accv[j] = ga[c][j];
+            } else {   // lane-consecutive -> 4 consecutive voxels per lane
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; j++) sX[32 * j + lane] = ga[c][j];
+                __syncwarp();
+                const float4 acc4 = *reinterpret_cast<const float4 *>(sX + 4 * lane);
+                accv[0] = acc4.x; accv[1] = acc4.y; accv[2] = acc4.z; accv[3] = acc4.w;
+            }
             float mv[4] = {m4.x, m4.y, m4.z, m4.w};
             float sv[4] = {s4.x, s4.y, s4.z, s4.w};
             float o[4], q[4];
@@ -205,12 +271,13 @@ __global__ void __launch_bounds__(128) bp4_kernel(RnDev p, Bp2Args a) {
             const int i0 = c * RN_CHUNK + 4 * lane;
             const float4 msg4 = make_float4(msg[0], msg[1], msg[2], msg[3]);
             if (c < NCH - 1 || i0 < L) rn_st_stream4_pol(m_row + i0, msg4, pol_stream);   // rows hold whole quads
-            *reinterpret_cast<float4 *>(sM + i0) = msg4;
+            __syncwarp();
+            *reinterpret_cast<float4 *>(sX + 4 * lane) = msg4;
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int i = c * RN_CHUNK + 32 * j + lane;
-                if (c < NCH - 1 || i < L) rn_red_add_pol(a.acc_out + sLin[i], sM[i], pol_keep);
+                if (c < NCH - 1 || i < L) rn_red_add_pol(a.acc_out + sLin[i], sX[32 * j + lane], pol_keep);
             }
         }
     }

@@ -388,7 +388,6 @@ struct Bp2Args {
     int nch_max;            // chunks of 128 voxels the shared-memory slots are sized for
     int rays_per_warp;      // bp4_kernel: consecutive rays one warp works through
     int uniform_acc;        // first sweep only: acc_in holds one value everywhere (the prior): no gathers needed
-    int debug;              // diagnostics only (RN_BP_DEBUG): 1 skip RED, 2 skip gathers, 4 skip message stores
 };
 
 // bytes of dynamic shared memory one warp needs for rays of up to nch chunks:

@@ -23,6 +23,7 @@ from .cuda_implementations.raynet_fp import perform_raynet_fp
 from .cuda_implementations.sample_points import compute_depth_from_distribution
 from .cuda_implementations.similarities import perform_multi_view_cnn_forward_pass_with_depth_estimation
 from .cuda_implementations.utils import device, to_gpu
+from . import sharding
 from .engine import RayPotentialEngine
 
 
@@ -184,22 +185,39 @@ class RayNetForwardPass(ForwardPass):
     Differences from the literal host loop of the reference (all behaviour-preserving, see the
     module docstring): features are computed ONCE per distinct view and uploaded once (the
     reference re-runs the CNN and re-uploads a re-ordered copy per reference image per sweep,
-    forward_pass.py:622-641); per-ray state never leaves the device; when a torch.distributed
-    process group is initialised, `images_range` selects THIS rank's reference images and the
-    occupancy accumulator is all-reduced after every sweep (raynet_b200/sharding.py).
+    forward_pass.py:622-641); per-ray state never leaves the device.
+
+    Memory.  The reference bounds its device memory with `rays_batch` (rays per launch) and spills
+    the messages to disk (forward_pass.py:588,602-611).  Here `rays_batch` is accepted for signature
+    compatibility and the bound is `memory_budget` (bytes; default 85 % of the free HBM): reference
+    images whose per-ray state does not fit are STREAMED -- their messages stay resident, their
+    voxel-space rows are recomputed on every sweep (engine.py) -- and a job that cannot fit even so
+    raises MemoryError before anything is launched.
+
+    Multi-GPU (a torch.distributed process group is initialised): `shard="rays"` (default) --
+    `images_range` names the WHOLE job on every rank; the (image, column-major pixel) ray enumeration
+    is cut into `world` contiguous blocks (sharding.image_segments), the occupancy accumulator is
+    all-reduced after every sweep and every rank yields the complete depth maps.  `shard="images"` --
+    `images_range` selects THIS rank's reference images (rank, n, world), only the accumulator is
+    shared and a rank yields its own images' maps.
 
     Feature hook: a `model` that has `predict_features(scene, view_indices)` is asked for the
-    (n, H+p+1, W+p+1, F) float32 maps of those views directly (e.g. a per-view feature cache, or
-    pinned host memory); otherwise the reference's `model.predict(stack of zero-padded images)`
-    is used."""
+    (n, H+p+1, W+p+1, F) float32 maps of those views directly (raynet_b200.models.SimpleCNN leaves
+    them on the device); otherwise the reference's `model.predict(stack of zero-padded images)` is
+    used.  Under shard="rays" the views are dealt out to the ranks, each rank runs the model on its
+    share and the maps are exchanged with one all-gather over NVLink."""
 
     def __init__(self, model, generation_params, sampling_scheme, image_shape, rays_batch, filter_out_rays=False,
-                 bp_iterations=3):
+                 bp_iterations=3, memory_budget=None, shard="rays", parity=False):
         super(RayNetForwardPass, self).__init__(model, generation_params, sampling_scheme, image_shape,
                                                 rays_batch, filter_out_rays)
+        assert shard in ("rays", "images")
         self.rays_batch = rays_batch
         self.ref_idx = -1
         self.bp_iterations = bp_iterations      # hard-coded to 3 in the reference (forward_pass.py:590)
+        self.memory_budget = memory_budget
+        self.shard = shard
+        self.parity = parity
         self.engine = None
         self._de = None
         self._feat_dev = None
@@ -227,36 +245,39 @@ class RayNetForwardPass(ForwardPass):
             self._staging[name] = buf
         return buf
 
-    def _ray_ids(self, ray_idxs, n_pixels, dev, k=0):
-        """Device int32 ray ids.  The usual case -- every pixel of the image is a ray
-        (forward_pass.py:168-179 without filtering) -- is generated on the device once and cached;
+    def _ray_ids(self, ray_idxs, first, last, n_pixels, dev, k=0):
+        """Device int32 ray ids of ray_idxs[first:last].  The usual case -- every pixel of the image is
+        a ray (forward_pass.py:168-179 without filtering) -- is generated on the device once and cached;
         filtered ray sets are uploaded through a pinned buffer."""
         if len(ray_idxs) == n_pixels and (n_pixels == 0 or (int(ray_idxs[0]) == 0 and int(ray_idxs[-1]) == n_pixels - 1)):
             ids = self._staging.get("all_pixels")
             if ids is None or ids.shape[0] != n_pixels:
                 ids = torch.arange(n_pixels, dtype=torch.int32, device=dev)
                 self._staging["all_pixels"] = ids
-            return ids
-        host = self._pinned("ray_ids_%d" % k, (len(ray_idxs),), torch.int32)   # one buffer per image: copies are asynchronous
-        host.numpy()[:] = ray_idxs
+            return ids[first:last]
+        host = self._pinned("ray_ids_%d" % k, (last - first,), torch.int32)   # one buffer per segment: copies are asynchronous
+        host.numpy()[:] = ray_idxs[first:last]
         self.h2d_bytes += host.numel() * 4
         return host.to(dev, non_blocking=True)
 
-    def _make_engine(self, scene, F, n_rays_total):
+    def _make_engine(self, scene, F, n_rays_total, max_segment):
         gp = self._generation_params
         vg = scene.voxel_grid(gp.grid_shape)
         M = int(gp.max_number_of_marched_voxels)
         eng = RayPotentialEngine(M, gp.depth_planes, gp.neighbors + 1, F, scene.image_shape[0],
                                  scene.image_shape[1], gp.padding, scene.bbox.ravel(), vg.shape[1:],
                                  gamma=gp.gamma_mrf if gp.gamma_mrf is not None else 0.05,
-                                 max_rays=n_rays_total)
+                                 max_rays=n_rays_total, parity=self.parity, memory_budget=self.memory_budget,
+                                 max_segment_rays=max_segment)
         eng.set_voxel_grid(vg)
         return eng
 
-    def _view_features(self, scene, views):
+    def _predict_views(self, scene, views):
         if hasattr(self._model, "predict_features"):
             f = self._model.predict_features(scene, views)
             if isinstance(f, torch.Tensor):
+                if f.is_cuda:
+                    self.h2d_bytes += int(getattr(self._model, "last_h2d_bytes", 0))
                 return f
             return torch.from_numpy(np.ascontiguousarray(f, dtype=np.float32))
         chunks = []
@@ -264,94 +285,170 @@ class RayNetForwardPass(ForwardPass):
             chunks.append(self._features([scene.get_image(v) for v in views[i:i + 5]]))
         return torch.from_numpy(np.concatenate(chunks, axis=0))
 
+    @staticmethod
+    def _view_orders(scene, img_ids):
+        """Scene indices of [reference, neighbours...] per reference image.  Scenes that know their
+        neighbour indices say so (`view_order(i)`: synth.SyntheticScene, common.scene.Scene); otherwise
+        the Image objects returned by get_image_with_neighbors are matched by identity against
+        scene.get_image(j) for the images of this call first, then the rest of the scene."""
+        if hasattr(scene, "view_order"):
+            return [list(scene.view_order(i)) for i in img_ids]
+        known = {}
+        for j in img_ids:
+            known[id(scene.get_image(j))] = j
+        orders, keep = [], []
+        for i in img_ids:
+            ims = scene.get_image_with_neighbors(i)
+            keep.append(ims)                     # keeps the objects alive: ids stay unique
+            if any(id(im) not in known for im in ims):
+                for j in range(scene.n_images):
+                    im = scene.get_image(j)
+                    keep.append(im)
+                    known.setdefault(id(im), j)
+            orders.append([known[id(im)] for im in ims])
+        return orders
+
     def forward_pass(self, scene, images_range):
         assert isinstance(images_range, tuple)
         (start_img_idx, end_img_idx, skip) = images_range
         H, W = scene.image_shape
         dev = device()
+        dist = torch.distributed
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank() if world > 1 else 0
+        by_rays = world > 1 and self.shard == "rays"
         img_ids = list(range(start_img_idx, end_img_idx, skip))
         rays = [self.get_valid_rays_per_image(scene, i) for i in img_ids]
-        total = int(sum(len(r) for r in rays))
         self.h2d_bytes = self.d2h_bytes = 0
-        # ---- features: once per distinct view --------------------------------------------------
-        # views are identified by object identity of the scene's cached Image objects
-        # (common/scene.py:171-177 caches them per index)
-        index_of = dict((id(scene.get_image(v)), v) for v in range(scene.n_images))
-        orders = [[index_of[id(im)] for im in scene.get_image_with_neighbors(i)] for i in img_ids]
-        views = sorted(set(v for o in orders for v in o))
+        # ---- this rank's segments: (position in img_ids, first ray, last ray) -------------------
+        if by_rays:
+            unit = 64 * H if all(len(r) % (64 * H) == 0 for r in rays) else 8 * H
+            segs = sharding.image_segments([len(r) for r in rays], rank, world, unit)
+        else:
+            segs = [(k, 0, len(r)) for k, r in enumerate(rays)]
+        total = int(sum(b - a for (_, a, b) in segs))
+        max_seg = max([b - a for (_, a, b) in segs] + [1])
+        # ---- features: once per distinct view ---------------------------------------------------
+        orders_all = self._view_orders(scene, img_ids)
+        views = sorted(set(v for (k, _, _) in segs for v in orders_all[k]))
         slot = dict((v, k) for k, v in enumerate(views))
-        f_host = self._view_features(scene, views)
         main = torch.cuda.current_stream(dev)
         copied = {}       # view slot -> event after which its feature map is on the device
-        if f_host.is_cuda:
-            # the model produced the feature volume on the device (raynet_b200.models.SimpleCNN): nothing to upload
-            self._feat_dev = f_host.contiguous()
-            self.h2d_bytes += int(getattr(self._model, "last_h2d_bytes", 0))
+        first_use = []
+        for (k, _, _) in segs:
+            first_use += [slot[v] for v in orders_all[k] if slot[v] not in first_use]
+        if by_rays and hasattr(self._model, "predict_features") and len(views) > 0:
+            # every rank needs (nearly) every view: deal the views out, run the model on this rank's share,
+            # exchange the maps with one all-gather (equal chunks of `per` view slots per rank)
+            all_views = sorted(set(v for o in orders_all for v in o))
+            per = -(-len(all_views) // world)
+            mine = all_views[rank * per:(rank + 1) * per]
+            part = self._predict_views(scene, mine) if mine else None
+            fshape = self._staging.get("feat_shape")
+            if fshape is None:                   # ranks without a view learn the map shape from the others, once
+                shapes = [None] * world
+                dist.all_gather_object(shapes, tuple(part.shape[1:]) if part is not None else None)
+                fshape = [s for s in shapes if s is not None][0]
+                self._staging["feat_shape"] = fshape
+            if self._feat_dev is None or tuple(self._feat_dev.shape) != (world * per,) + tuple(fshape):
+                self._feat_dev = torch.empty((world * per,) + tuple(fshape), dtype=torch.float32, device=dev)
+            if part is not None:
+                self._feat_dev[rank * per:rank * per + len(mine)].copy_(part.to(dev, non_blocking=True))
+            dist.all_gather_into_tensor(self._feat_dev, self._feat_dev[rank * per:(rank + 1) * per])
+            slot = dict((v, k) for k, v in enumerate(all_views))
+            n_slots = world * per
         else:
-            if self._feat_dev is None or self._feat_dev.shape != f_host.shape:
-                self._feat_dev = torch.empty(f_host.shape, dtype=torch.float32, device=dev)
-            # the feature maps travel on a copy stream, view by view in the order the reference images
-            # need them, while the rays are traced and binned (neither needs them); the similarity of an
-            # image waits only for the views it reads
-            if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream(device=dev)
-            self._copy_stream.wait_stream(main)      # the previous call's readers of _feat_dev are done
-            first_use = []
-            for o in orders:
-                first_use += [slot[v] for v in o if slot[v] not in first_use]
-            with torch.cuda.stream(self._copy_stream):
-                for k in first_use:
-                    self._feat_dev[k].copy_(f_host[k], non_blocking=True)
-                    copied[k] = torch.cuda.Event()
-                    copied[k].record()
-            self.h2d_bytes += f_host.numel() * 4
-        if self.engine is None or self.engine.capacity < total:
-            self.engine = self._make_engine(scene, f_host.shape[-1], total)
+            f_host = self._predict_views(scene, views)
+            n_slots = len(views)
+            if f_host.is_cuda:
+                # the model produced the feature volume on the device (raynet_b200.models.SimpleCNN): nothing to upload
+                self._feat_dev = f_host.contiguous()
+            else:
+                if self._feat_dev is None or self._feat_dev.shape != f_host.shape:
+                    self._feat_dev = torch.empty(f_host.shape, dtype=torch.float32, device=dev)
+                # the feature maps travel on a copy stream, view by view in the order the reference images
+                # need them, while the rays are traced and binned (neither needs them); the similarity of an
+                # image waits only for the views it reads.  Pageable sources are staged through pinned memory
+                # (a pageable non_blocking copy blocks the host and nothing would overlap).
+                if not f_host.is_pinned():
+                    stage = self._pinned("features", tuple(f_host.shape), torch.float32)
+                    stage.copy_(f_host)
+                    f_host = stage
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=dev)
+                self._copy_stream.wait_stream(main)      # the previous call's readers of _feat_dev are done
+                with torch.cuda.stream(self._copy_stream):
+                    for k in first_use:
+                        self._feat_dev[k].copy_(f_host[k], non_blocking=True)
+                        copied[k] = torch.cuda.Event()
+                        copied[k].record()
+                self.h2d_bytes += f_host.numel() * 4
+        F = int(self._feat_dev.shape[-1])
+        if self.engine is None or self.engine.capacity < total or self.engine.max_segment_rays < min(max_seg, total):
+            self.engine = None                     # release the old state before the larger one is allocated
+            self.engine = self._make_engine(scene, F, total, max_seg)
         else:
             self.engine.reset()
-        # ---- front end, first half: trace the rays of every reference image, bin them ----------
+        # ---- front end, first half: trace the rays of every segment, bin them --------------------
         # all camera matrices and view slots travel in ONE pinned buffer (pageable uploads block the
         # host for ~0.5 ms each and would leave the GPU idle between the per-image launches)
-        n_img = len(img_ids)
-        nV = len(orders[0])
+        n_seg = len(segs)
+        nV = len(orders_all[0])
         stride = 12 * nV + 16
-        meta = self._pinned("cams", (n_img, stride), torch.float32)
-        vids = self._pinned("view_ids", (n_img, nV), torch.int32)
-        for k, ref_idx in enumerate(img_ids):
-            images = scene.get_image_with_neighbors(ref_idx)
+        meta = self._pinned("cams", (max(n_seg, 1), stride), torch.float32)
+        vids = self._pinned("view_ids", (max(n_seg, 1), nV), torch.int32)
+        for j, (k, _, _) in enumerate(segs):
+            images = scene.get_image_with_neighbors(img_ids[k])
             assert len(images) == nV
-            row = meta[k].numpy()
+            row = meta[j].numpy()
             row[:12 * nV] = np.array([im.camera.P for im in images], dtype=np.float32).ravel()
             row[12 * nV:12 * nV + 12] = np.asarray(images[0].camera.P_pinv, dtype=np.float32).ravel()
             row[12 * nV + 12:] = np.asarray(images[0].camera.center, dtype=np.float32).ravel()[:4]
-            vids[k] = torch.tensor([slot[v] for v in orders[k]], dtype=torch.int32)
+            vids[j] = torch.tensor([slot[v] for v in orders_all[k]], dtype=torch.int32)
         meta_dev = meta.to(dev, non_blocking=True)
         vids_dev = vids.to(dev, non_blocking=True)
         self.h2d_bytes += meta.numel() * 4 + vids.numel() * 4
-        per_image = []
-        for k, ref_idx in enumerate(img_ids):
-            ids = self._ray_ids(rays[k], H * W, dev, k)
+        per_seg = []
+        for j, (k, a, b) in enumerate(segs):
+            ids = self._ray_ids(rays[k], a, b, H * W, dev, j)
             nP = 12 * nV
-            self.engine.trace_image(ids, meta_dev[k, nP:nP + 12], meta_dev[k, nP + 12:nP + 16])
-            per_image.append((meta_dev[k, :nP], vids_dev[k]))
+            self.engine.trace_image(ids, meta_dev[j, nP:nP + 12], meta_dev[j, nP + 12:nP + 16])
+            per_seg.append((meta_dev[j, :nP], vids_dev[j]))
         self.engine.finalize_frontend()
         self.d2h_bytes += 4
-        # ---- front end, second half: similarity + plane->voxel mapping per reference image -----
-        for k, (P_dev, view_ids) in enumerate(per_image):
-            for v in orders[k]:
+        # ---- front end, second half: similarity + plane->voxel mapping per segment ----------------
+        for j, (P_dev, view_ids) in enumerate(per_seg):
+            for v in orders_all[segs[j][0]]:
                 if slot[v] in copied:
                     main.wait_event(copied.pop(slot[v]))
-            self.engine.score_image(k, self._feat_dev, P_dev, view_ids=view_ids, n_feature_slots=len(views))
+            self.engine.score_image(j, self._feat_dev, P_dev, view_ids=view_ids, n_feature_slots=n_slots)
         # ---- BP sweeps + depth -----------------------------------------------------------------
         self.engine.run_bp(self.bp_iterations)
-        depth_dev = self.engine.depth()
+        if by_rays:
+            # every rank yields complete maps: this rank's block goes into a zeroed job-sized buffer, one SUM
+            # all-reduce (x + 0 is exact) completes it everywhere
+            job_total = int(sum(len(r) for r in rays))
+            offs = np.concatenate([[0], np.cumsum([len(r) for r in rays])])
+            depth_dev = self._staging.get("depth_job")
+            if depth_dev is None or depth_dev.shape[0] != job_total:
+                depth_dev = torch.empty((job_total,), dtype=torch.float32, device=dev)
+                self._staging["depth_job"] = depth_dev
+            depth_dev.zero_()
+            if segs:
+                lo = int(offs[segs[0][0]] + segs[0][1])
+                self.engine.depth(depth_out=depth_dev[lo:lo + total])
+            dist.all_reduce(depth_dev, op=dist.ReduceOp.SUM)
+            seg_of = [(int(offs[k]), len(rays[k])) for k in range(len(img_ids))]
+        else:
+            depth_dev = self.engine.depth()
+            seg_of = [(self.engine.segments[k][0], self.engine.segments[k][1]) for k in range(len(img_ids))]
         depth_host = self._pinned("depth", (int(depth_dev.shape[0]),), torch.float32)
         depth_host.copy_(depth_dev, non_blocking=True)       # pinned destination: one DMA, no staging copy
         torch.cuda.current_stream(dev).synchronize()
         depth = depth_host.numpy().copy()
         self.d2h_bytes += depth.nbytes
         for k, ref_idx in enumerate(img_ids):
-            start, n, _ = self.engine.segments[k]
+            start, n = seg_of[k]
             if len(rays[k]) == H * W:
                 d = depth[start:start + n]
             else:

@@ -34,6 +34,7 @@ class SimpleCNN(object):
         self.launches = 0
         self._scratch = None      # two device buffers for the intermediate layers
         self.last_h2d_bytes = 0   # bytes of zero-padded images uploaded by the last predict_features()
+        self._staging = None      # pinned host buffer of the zero-padded views
 
     # ------------------------------------------------------------------ weights
     @classmethod
@@ -123,12 +124,17 @@ class SimpleCNN(object):
 
     def predict_features(self, scene, view_indices, padding=11):
         """RayNetForwardPass hook: feature maps of the given views as ONE CUDA tensor
-        [n, H+padding+1, W+padding+1, 32] (zero-padding as forward_pass.py:181-198)."""
+        [n, H+padding+1, W+padding+1, 32] (zero-padding as forward_pass.py:181-198).  The zero-padded views
+        are assembled in a cached pinned buffer (its border stays zero) and uploaded with one DMA."""
         images = [scene.get_image(v).image for v in view_indices]
         H, W, C = images[0].shape
-        X = torch.zeros((len(images), H + 2 * padding, W + 2 * padding, C), dtype=torch.float32).pin_memory()
+        shape = (len(images), H + 2 * padding, W + 2 * padding, C)
+        X = self._staging
+        if X is None or tuple(X.shape) != shape:
+            X = self._staging = torch.zeros(shape, dtype=torch.float32).pin_memory()
+        inner = X.numpy()[:, padding:padding + H, padding:padding + W, :]
         for k, im in enumerate(images):
-            X[k, padding:padding + H, padding:padding + W, :] = torch.from_numpy(np.ascontiguousarray(im, dtype=np.float32))
+            inner[k] = im
         self.last_h2d_bytes = X.numel() * 4
         return self.predict_device(X.to(device(), non_blocking=True))
 

@@ -5,10 +5,13 @@ from .. import _lib
 from ..cuda_implementations.utils import all_arrays_to_gpu, current_stream_ptr, ptr, to_gpu
 
 
-def batch_ray_belief_propagation(M, grid_shape):
-    """mrf_cuda.py:12-124.  Returns (bp, de)."""
+def batch_ray_belief_propagation(M, grid_shape, parity=False):
+    """mrf_cuda.py:12-124.  Returns (bp, de).  parity=True: the accumulators are float64 device arrays
+    and the kernels follow mrf_np.py as it executes under NumPy >= 2 (csrc/rn_parity.cuh)."""
     grid_shape = tuple(int(g) for g in np.asarray(grid_shape).ravel())
     params = _lib.make_params(M=M, grid_shape=grid_shape)
+    acc_dtype = np.float64 if parity else np.float32
+    suffix = "_f64" if parity else ""
 
     @all_arrays_to_gpu
     def bp(S, ray_voxel_indices, ray_voxel_count, ray_to_occupancy_accumulated_pon,
@@ -26,7 +29,8 @@ def batch_ray_belief_propagation(M, grid_shape):
         assert np.float32 == ray_to_occupancy_messages_pon.dtype
         assert np.int32 == ray_voxel_indices.dtype
         assert np.int32 == ray_voxel_count.dtype
-        _lib.call("rn_bp_iteration", params, ptr(S), ptr(ray_voxel_indices), ptr(ray_voxel_count),
+        assert acc_dtype == ray_to_occupancy_accumulated_pon.dtype == ray_to_occupancy_accumulated_out_pon.dtype
+        _lib.call("rn_bp_iteration" + suffix, params, ptr(S), ptr(ray_voxel_indices), ptr(ray_voxel_count),
                   ptr(ray_to_occupancy_accumulated_pon), ptr(ray_to_occupancy_messages_pon),
                   ptr(ray_to_occupancy_accumulated_out_pon), len(S), current_stream_ptr())
         return ray_to_occupancy_accumulated_out_pon, ray_to_occupancy_messages_pon
@@ -48,7 +52,8 @@ def batch_ray_belief_propagation(M, grid_shape):
         assert np.float32 == ray_to_occupancy_messages_pon.dtype
         assert np.int32 == ray_voxel_indices.dtype
         assert np.int32 == ray_voxel_count.dtype
-        _lib.call("rn_depth_estimate", params, ptr(S), ptr(ray_voxel_indices), ptr(ray_voxel_count),
+        assert acc_dtype == ray_to_occupancy_accumulated_pon.dtype
+        _lib.call("rn_depth_estimate" + suffix, params, ptr(S), ptr(ray_voxel_indices), ptr(ray_voxel_count),
                   ptr(ray_to_occupancy_accumulated_pon), ptr(ray_to_occupancy_messages_pon), ptr(S_new),
                   len(S), current_stream_ptr())
         return S_new
@@ -57,14 +62,16 @@ def batch_ray_belief_propagation(M, grid_shape):
 
 
 def belief_propagation(S, ray_voxel_indices, ray_voxel_count, ray_to_occupancy_messages_pon, grid_shape,
-                       gamma=0.05, bp_iterations=3, batch_size=50000):
-    """mrf_cuda.py:127-197.  Host arrays in, (accumulated ndarray f32[grid], messages ndarray) out."""
+                       gamma=0.05, bp_iterations=3, batch_size=50000, parity=False):
+    """mrf_cuda.py:127-197.  Host arrays in, (accumulated ndarray f32[grid], messages ndarray) out.
+    parity=True (extension): float64 accumulators like mrf_np.py under NumPy >= 2; returns float64."""
     N, M = S.shape
     ray_to_occupancy_messages_pon.fill(0)
     prior = np.log(gamma) - np.log(1 - gamma)
-    acc = to_gpu(np.full(tuple(grid_shape), prior, dtype=np.float32))
-    acc_out = to_gpu(np.full(tuple(grid_shape), prior, dtype=np.float32))
-    bp, _ = batch_ray_belief_propagation(M, grid_shape)
+    dt = np.float64 if parity else np.float32
+    acc = to_gpu(np.full(tuple(grid_shape), prior, dtype=dt))
+    acc_out = to_gpu(np.full(tuple(grid_shape), prior, dtype=dt))
+    bp, _ = batch_ray_belief_propagation(M, grid_shape, parity=parity)
     for it in range(bp_iterations):
         for i in range(0, N, batch_size):
             _, msgs = bp(S[i:i + batch_size], ray_voxel_indices[i:i + batch_size],
@@ -77,12 +84,12 @@ def belief_propagation(S, ray_voxel_indices, ray_voxel_count, ray_to_occupancy_m
 
 
 def compute_depth_distribution(S, ray_voxel_indices, ray_voxel_count, ray_to_occupancy_messages_pon,
-                               ray_to_occupancy_accumulated_pon, S_new, grid_shape, batch_size=50000):
+                               ray_to_occupancy_accumulated_pon, S_new, grid_shape, batch_size=50000, parity=False):
     """mrf_cuda.py:200-251."""
     N, M = S.shape
     S_new.fill(0)
-    _, de = batch_ray_belief_propagation(M, grid_shape)
-    acc = to_gpu(np.ascontiguousarray(ray_to_occupancy_accumulated_pon, dtype=np.float32))
+    _, de = batch_ray_belief_propagation(M, grid_shape, parity=parity)
+    acc = to_gpu(np.ascontiguousarray(ray_to_occupancy_accumulated_pon, dtype=np.float64 if parity else np.float32))
     for i in range(0, N, batch_size):
         s = de(S[i:i + batch_size], ray_voxel_indices[i:i + batch_size], ray_voxel_count[i:i + batch_size],
                acc, ray_to_occupancy_messages_pon[i:i + batch_size], S_new[i:i + batch_size])
@@ -91,8 +98,10 @@ def compute_depth_distribution(S, ray_voxel_indices, ray_voxel_count, ray_to_occ
 
 
 def compute_occupancy_probabilities(ray_to_occupancy_accumulated_pon, gamma=0.031):
-    """mrf_np.py:206-240 on the device: sigmoid of the accumulated log-odds."""
-    acc = to_gpu(np.ascontiguousarray(ray_to_occupancy_accumulated_pon, dtype=np.float32))
+    """mrf_np.py:206-240 on the device: sigmoid of the accumulated log-odds (in the array's own
+    precision, like the numpy code: float64 accumulators give a float64 sigmoid)."""
+    f64 = np.asarray(ray_to_occupancy_accumulated_pon).dtype == np.float64
+    acc = to_gpu(np.ascontiguousarray(ray_to_occupancy_accumulated_pon, dtype=np.float64 if f64 else np.float32))
     out = to_gpu(np.zeros(acc.shape, dtype=np.float32))
-    _lib.call("rn_occupancy", ptr(acc), ptr(out), acc.size, current_stream_ptr())
+    _lib.call("rn_occupancy_f64" if f64 else "rn_occupancy", ptr(acc), ptr(out), acc.size, current_stream_ptr())
     return out.get()

@@ -28,12 +28,26 @@ def ray_block(n_rays, rank, world):
     return start, stop
 
 
-def image_segments(rays_per_image, rank, world):
+def aligned_ray_block(n_rays, rank, world, unit=1):
+    """ray_block() with the interior boundaries rounded to multiples of `unit` rays (whole groups of
+    image columns keep the tiled ray enumeration of the kernels usable inside partial images).
+    Falls back to unit = 1 when n_rays is not a multiple of unit.  Every ray is owned exactly once."""
+    n_rays, unit = int(n_rays), int(unit)
+    if unit <= 1 or n_rays % unit != 0:
+        return ray_block(n_rays, rank, world)
+    a, b = ray_block(n_rays // unit, rank, world)
+    return a * unit, b * unit
+
+
+def image_segments(rays_per_image, rank, world, unit=1):
     """Split the concatenation of the images' ray lists into `world` contiguous blocks and
     return this rank's pieces as [(image_position, first, last_exclusive), ...] where first /
-    last index into that image's ray list.  `rays_per_image`: list of ints."""
+    last index into that image's ray list.  `rays_per_image`: list of ints.  unit: see
+    aligned_ray_block (used only when every image is a multiple of it)."""
     total = int(sum(rays_per_image))
-    start, stop = ray_block(total, rank, world)
+    if unit > 1 and any(int(n) % unit for n in rays_per_image):
+        unit = 1
+    start, stop = aligned_ray_block(total, rank, world, unit)
     out, off = [], 0
     for k, n in enumerate(rays_per_image):
         a, b = max(start, off), min(stop, off + n)

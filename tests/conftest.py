@@ -28,3 +28,34 @@ def ref_mods(oracle):
     except Exception:
         pass
     return oracle.ref_modules()
+
+
+_PARITY_LOG = {}
+
+
+@pytest.fixture(scope="session")
+def parity_log():
+    """Measured parity errors, recorded by the GPU tests and written to gpurun_out/r02_parity.json at the end
+    of the session (committed as profiles/r02_parity.json)."""
+    return _PARITY_LOG
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY_LOG:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, "r02_parity.json")
+        old = {}
+        if os.path.exists(path):
+            try:
+                old = json.load(open(path))
+            except Exception:
+                old = {}
+        old.update(_PARITY_LOG)
+        with open(path, "w") as f:
+            json.dump(old, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

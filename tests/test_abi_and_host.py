@@ -31,7 +31,7 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, s), "symbol %s declared in the header is not exported" % s
     # and the ctypes table covers the header exactly
     assert sorted(list(_lib.SIGNATURES) + _lib.OTHER_SYMBOLS) == syms
-    assert lib.rn_abi_version() == 2
+    assert lib.rn_abi_version() == 3
     assert lib.rn_row_stride(96) == 128 and lib.rn_row_stride(768) == 768 and lib.rn_num_classes() == 13
     assert lib.rn_code_stride(768) == 192 and lib.rn_code_stride(96) == 32 and lib.rn_code_stride(1) == 32
 
@@ -91,6 +91,21 @@ def test_ray_blocks_partition():
     covered = sorted((k, i) for s in segs for (k, a, b) in s for i in range(a, b))
     assert covered == [(k, i) for k in range(3) for i in range(10)]
     assert sharding.images_of_rank(72, 3, 8) == list(range(27, 36))
+    # aligned blocks (whole groups of image columns): C3's 9 x 512 x 512 rays over 8 ranks in units of 64 columns
+    H, n_img = 512, 9
+    for world in (1, 2, 4, 8, 3):
+        segs = [sharding.image_segments([H * H] * n_img, r, world, 64 * H) for r in range(world)]
+        flat = [(k, a, b) for sg in segs for (k, a, b) in sg]
+        assert all(a % (64 * H) == 0 and b % (64 * H) == 0 for (_, a, b) in flat)
+        assert sum(b - a for (_, a, b) in flat) == n_img * H * H
+        per_rank = [sum(b - a for (_, a, b) in sg) for sg in segs]
+        assert max(per_rank) - min(per_rank) <= 64 * H
+        for k in range(n_img):      # every image covered exactly once, in order
+            pieces = sorted((a, b) for (kk, a, b) in flat if kk == k)
+            assert pieces[0][0] == 0 and pieces[-1][1] == H * H
+            assert all(pieces[i][1] == pieces[i + 1][0] for i in range(len(pieces) - 1))
+    assert sharding.aligned_ray_block(1000, 1, 3, 64) == sharding.ray_block(1000, 1, 3)      # not a multiple: unit 1
+    assert sharding.image_segments([100, 64], 0, 2, 64) == sharding.image_segments([100, 64], 0, 2, 1)
     assert sharding.seed_value(0, -2.5) == -2.5 and sharding.seed_value(3, -2.5) == 0.0
 
 

@@ -36,6 +36,17 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """Experiment builds (scripts/gpu_variants.sh): the same library with -D overrides of the tuning macros,
+    written to raynet_b200/variants/<name>.so; a run copies one over libraynet_b200.so."""
+    out_dir = os.path.join(HERE, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, name + ".so")
+    cmd = [os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out, SRC]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)

@@ -51,6 +51,9 @@ __device__ __forceinline__ float rn_occ_w2(float acc, float msg) {
 #ifndef RN_BP4_RAYS_PER_WARP
 #define RN_BP4_RAYS_PER_WARP 8
 #endif
+#ifndef RN_BP4_WAIT_ONE
+#define RN_BP4_WAIT_ONE 0
+#endif
 #ifndef RN_BP4_TMA
 #define RN_BP4_TMA 1      // 1: rows staged by cp.async.bulk + mbarrier (TMA); 0: by per-lane 16-byte cp.async (LDGSTS)
 #endif
@@ -153,8 +156,16 @@ __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp
         } else if (!kTma) {
             rn_cp_async_wait<0>();
         }
-        if (kTma) rn_mbar_wait(rn_smem_u32(&bars[wid][b]), (uint32_t)((t >> 1) & 1));   // buffer b: use number t / 2
-        else __syncwarp();   // ... and every lane's copies of ray t have landed
+        if (kTma) {
+#if RN_BP4_WAIT_ONE
+            if (lane == 0) rn_mbar_wait(rn_smem_u32(&bars[wid][b]), (uint32_t)((t >> 1) & 1));
+            __syncwarp();
+#else
+            rn_mbar_wait(rn_smem_u32(&bars[wid][b]), (uint32_t)((t >> 1) & 1));   // buffer b: use number t / 2
+#endif
+        } else {
+            __syncwarp();   // ... and every lane's copies of ray t have landed
+        }
         const int *sLin = reinterpret_cast<const int *>(base + b * ROW);
         const float *sS = base + (2 + b) * ROW;
         const float *sM = base + (4 + b) * ROW;   // !kFirst only

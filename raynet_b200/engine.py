@@ -420,9 +420,13 @@ class RayPotentialEngine(object):
         self.iterations_done = max(self.iterations_done, 1)
 
     def messages(self):
+        """Messages [n_rays, M]; slots beyond a ray's count (and the rows of the rays BP skips) read 0 like the
+        reference's zero-initialised array -- the kernels never touch them."""
         if self.iterations_done == 0:
             return torch.zeros((self.n_rays, self.M), dtype=torch.float32, device=self.dev)
-        return self.msgs[:self.n_rays, :self.M]
+        cnt = self.count[:self.n_rays]
+        live = torch.arange(self.M, device=self.dev)[None, :] < torch.where(cnt > 1, cnt, torch.zeros_like(cnt))[:, None]
+        return torch.where(live, self.msgs[:self.n_rays, :self.M], torch.zeros((), dtype=torch.float32, device=self.dev))
 
     # ------------------------------------------------------------------ outputs
     def depth(self, depth_out=None, S_new=None):

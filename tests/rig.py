@@ -63,6 +63,12 @@ def case_nine(**kw):
     return Case(64, 9, 64, 40, 40, 192, n_rays=1000, **kw)
 
 
+def case_dense(**kw):
+    """SURVEY.md 7's probe: a 32^3 grid crossed by every pixel of 64x64 images from 4 views -- ~20 rays per
+    voxel, accumulators far from 0, the setting in which BP amplifies a last-digit difference most."""
+    return Case(32, 4, 16, 64, 64, 96, **kw)
+
+
 def sigmoid(x):
     x = np.asarray(x, np.float64)
     return 1.0 / (1.0 + np.exp(-x))

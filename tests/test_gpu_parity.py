@@ -12,7 +12,7 @@ Gates (BASELINE.json north_star / SURVEY.md 8d):
 import numpy as np
 import pytest
 
-from rig import Case, case_c1, case_long, case_nine, case_small, case_xlong, sigmoid
+from rig import Case, case_c1, case_dense, case_long, case_nine, case_small, case_xlong, sigmoid
 
 pytestmark = pytest.mark.gpu
 
@@ -438,7 +438,7 @@ def _run_engine(torch, c, iters, refs=None, parity=False, memory_budget=None, sp
 
 
 @pytest.mark.parametrize("mk,iters", [(case_c1, 3), (case_c1, 5), (case_small, 3), (case_small, 5), (case_long, 2),
-                                      (case_nine, 2), (case_nine, 5), (case_xlong, 2)])
+                                      (case_nine, 2), (case_nine, 5), (case_xlong, 2), (case_dense, 5)])
 def test_engine_end_to_end_vs_oracle(torch_cuda, oracle, mk, iters, parity_log):
     """C1 (and longer-ray cases) through the resident pipeline: every view a reference view in
     turn, I sweeps, depth pass -- against the oracle run the same way.  PARITY MODE must be within

@@ -329,6 +329,47 @@ int rn_engine_depth_f64(const RnParams *p, const int32_t *lin, const int32_t *co
                         const int64_t *seg_starts, int32_t n_seg, float *depth_map, float *S_new, int64_t n_rays,
                         void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * SURVEY.md 8(f) row 3 -- backward pass through the unrolled BP (training).  The reference lets TensorFlow
+ * differentiate its graph (tf_implementations/forward_backward_pass.py:128-248, mrf/mrf_tf.py:60-271); here
+ * the adjoint of each stage is a kernel over the same buffers (voxel lists int32 [n][M][3], rows float32
+ * [n][M], accumulators float32 [Gx][Gy][Gz]).  The caller keeps the inputs of every forward sweep (messages,
+ * accumulator) as checkpoints and walks them backwards; raynet_b200/training.py does exactly that.
+ * scratch: caller-owned float64 scratch, any size >= rn_backward_scratch_bytes(p, 1); the rays are processed
+ * in chunks that fit.  Gradient buffers marked += are accumulated into (zero them first).
+ * ------------------------------------------------------------------------------------- */
+int64_t rn_backward_scratch_bytes(const RnParams *p, int64_t n_rays);
+/* adjoint of one sweep (rn_bp_iteration; mrf_tf.py:60-143): msg_in may be NULL (first sweep, all zero);
+ * g_msg_out (direct gradient w.r.t. the sweep's output messages) and g_acc_next (gradient w.r.t. the
+ * accumulator prior + sum of those messages) may be NULL; g_s += gradient w.r.t. S_norm =
+ * clip_and_renorm(S); g_msg_in = gradient w.r.t. msg_in (may alias g_msg_out); g_acc_in += (atomic). */
+int rn_bp_sweep_backward(const RnParams *p, const float *S, const int32_t *ray_voxel_indices, const int32_t *ray_voxel_count,
+                         const float *acc_in, const float *msg_in, const float *g_msg_out, const float *g_acc_next,
+                         float *g_s, float *g_msg_in, float *g_acc_in, double *scratch, int64_t scratch_bytes,
+                         int64_t n_rays, void *stream);
+/* adjoint of rn_depth_estimate (mrf_tf.py:146-173): g_S_new [n][M] in; g_s +=, g_msgs =, g_acc += out. */
+int rn_depth_estimate_backward(const RnParams *p, const float *S, const int32_t *ray_voxel_indices,
+                               const int32_t *ray_voxel_count, const float *acc, const float *msgs, const float *g_S_new,
+                               float *g_s, float *g_msgs, float *g_acc, double *scratch, int64_t scratch_bytes,
+                               int64_t n_rays, void *stream);
+/* adjoint of [clip_and_renorm (mrf_tf.py:6-15) +] rn_planes_to_voxels (planes_voxels_mapping.cu:6-92,
+ * forward_backward_pass.py:76-125) + softmax.  g_in [n][M]: the gradient w.r.t. S_norm, or, with
+ * g_is_wrt_S_voxel_space != 0, w.r.t. S_voxel_space (the clip_and_renorm adjoint already applied, e.g. by
+ * rn_clip_renorm_backward).  Out: g_S_voxel_space [n][M] (may be NULL), g_S_planes [n][D], g_scores [n][D]
+ * (may be NULL; the gradient w.r.t. the softmax input). */
+int rn_planes_to_voxels_backward(const RnParams *p, const float *voxel_grid, const int32_t *ray_voxel_indices,
+                                 const int32_t *ray_voxel_count, const float *starts, const float *ends,
+                                 const float *S_planes, const float *g_in, int32_t g_is_wrt_S_voxel_space,
+                                 float *g_S_voxel_space, float *g_S_planes, float *g_scores, int64_t n_rays, void *stream);
+/* adjoint of clip_and_renorm alone: g_s_norm -> gradient w.r.t. the raw rows S. */
+int rn_clip_renorm_backward(const RnParams *p, const float *S, const int32_t *ray_voxel_count, const float *g_s_norm,
+                            float *g_S, int64_t n_rays, void *stream);
+/* losses of tf_implementations/loss_functions.py:4-35 per ray + gradient w.r.t. y_pred times `scale`:
+ * kind 0 emd, 1 squared_emd, 2 expected_squared_error (needs voxel lists, voxel_grid, camera centres [n][4]). */
+int rn_depth_loss(const RnParams *p, int32_t kind, const float *y_true, const float *y_pred,
+                  const int32_t *ray_voxel_indices, const float *voxel_grid, const float *camera_centres, float *loss,
+                  float *g_pred, float scale, int64_t n_rays, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

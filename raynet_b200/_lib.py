@@ -91,9 +91,15 @@ SIGNATURES = {
     "rn_depth_estimate_f64": [_PP, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _PTR],
     "rn_engine_bp_iteration_f64": [_PP] + [_PTR] * 6 + [_I32, _I64, _PTR],
     "rn_engine_depth_f64": [_PP] + [_PTR] * 8 + [_I32, _PTR, _PTR, _I64, _PTR],
+    # backward pass (training)
+    "rn_bp_sweep_backward": [_PP] + [_PTR] * 11 + [_I64, _I64, _PTR],
+    "rn_depth_estimate_backward": [_PP] + [_PTR] * 10 + [_I64, _I64, _PTR],
+    "rn_planes_to_voxels_backward": [_PP] + [_PTR] * 7 + [_I32] + [_PTR] * 3 + [_I64, _PTR],
+    "rn_clip_renorm_backward": [_PP] + [_PTR] * 4 + [_I64, _PTR],
+    "rn_depth_loss": [_PP, _I32] + [_PTR] * 7 + [ctypes.c_float, _I64, _PTR],
 }
 OTHER_SYMBOLS = ["rn_last_error", "rn_abi_version", "rn_device_info", "rn_code_stride", "rn_row_stride", "rn_num_classes",
-                 "rn_brick_elems"]
+                 "rn_brick_elems", "rn_backward_scratch_bytes"]
 
 _lib = None
 
@@ -129,6 +135,8 @@ def load():
     lib.rn_num_classes.argtypes = []
     lib.rn_brick_elems.restype = ctypes.c_int64
     lib.rn_brick_elems.argtypes = [_PP]
+    lib.rn_backward_scratch_bytes.restype = ctypes.c_int64
+    lib.rn_backward_scratch_bytes.argtypes = [_PP, _I64]
     _lib = lib
     return lib
 

@@ -8,6 +8,7 @@
 #include "rn_kernels.cuh"
 #include "rn_bp4.cuh"
 #include "rn_parity.cuh"
+#include "rn_backward.cuh"
 #include "rn_simmap3.cuh"
 #include "rn_cnn.cuh"
 #include "rn_fusion.cuh"
@@ -85,6 +86,7 @@ int make_dev(const RnParams *p, RnDev &d, bool need_grid, bool need_views, bool 
 }
 
 inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+inline cudaStream_t S_(void *s) { return reinterpret_cast<cudaStream_t>(s); }   // where a parameter is called S
 
 // Largest dynamic shared memory size a kernel has been opted into, PER DEVICE (the attribute is per
 // device; a process may drive several).  Races are benign: the worst case sets the attribute twice.
@@ -863,6 +865,125 @@ int rn_engine_depth_f64(const RnParams *p, const int32_t *lin, const int32_t *co
     a.depth_map = depth_map; a.S_new = S_new; a.n_rays = n_rays;
     depth_parity_kernel<false><<<(unsigned)((n_rays + 3) / 4), 128, 0, S(stream)>>>(d, a);
     return check_launch("depth_parity_kernel");
+}
+
+// ---- backward pass through the unrolled BP (rn_backward.cuh) --------------------------
+int64_t rn_backward_scratch_bytes(const RnParams *p, int64_t n_rays) {
+    if (!p || p->max_voxels <= 0 || n_rays < 0) return -1;
+    return (int64_t)RN_BWD_SLOTS * p->max_voxels * n_rays * (int64_t)sizeof(double);
+}
+
+static int64_t bwd_chunk(const RnDev &d, int64_t scratch_bytes) {
+    return scratch_bytes / ((int64_t)RN_BWD_SLOTS * d.M * (int64_t)sizeof(double));
+}
+
+int rn_bp_sweep_backward(const RnParams *p, const float *S, const int32_t *ray_voxel_indices, const int32_t *ray_voxel_count,
+                         const float *acc_in, const float *msg_in, const float *g_msg_out, const float *g_acc_next,
+                         float *g_s, float *g_msg_in, float *g_acc_in, double *scratch, int64_t scratch_bytes,
+                         int64_t n_rays, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    if (n_rays <= 0) return RN_OK;
+    if (!S || !ray_voxel_indices || !ray_voxel_count || !acc_in || !g_s || !g_msg_in || !g_acc_in || !scratch)
+        return fail(RN_ERR_SHAPE, "rn_bp_sweep_backward: NULL buffer");
+    const int64_t chunk = bwd_chunk(d, scratch_bytes);
+    if (chunk < 1) return fail(RN_ERR_SHAPE, "rn_bp_sweep_backward: scratch too small for one ray (%lld bytes needed)",
+                               (long long)rn_backward_scratch_bytes(p, 1));
+    BwdArgs a = {};
+    a.S = S; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc_in = acc_in; a.msg_in = msg_in;
+    a.g_out = g_msg_out; a.g_acc_next = g_acc_next; a.g_s = g_s; a.g_msg_in = g_msg_in; a.g_acc_in = g_acc_in;
+    a.scratch = scratch;
+    for (int64_t first = 0; first < n_rays; first += chunk) {
+        a.first = first;
+        a.n = (n_rays - first < chunk) ? n_rays - first : chunk;
+        bp_sweep_bwd_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, S_(stream)>>>(d, a);
+        if ((rc = check_launch("bp_sweep_bwd_kernel"))) return rc;
+    }
+    return RN_OK;
+}
+
+int rn_depth_estimate_backward(const RnParams *p, const float *S, const int32_t *ray_voxel_indices,
+                               const int32_t *ray_voxel_count, const float *acc, const float *msgs, const float *g_S_new,
+                               float *g_s, float *g_msgs, float *g_acc, double *scratch, int64_t scratch_bytes,
+                               int64_t n_rays, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    if (n_rays <= 0) return RN_OK;
+    if (!S || !ray_voxel_indices || !ray_voxel_count || !acc || !msgs || !g_S_new || !g_s || !g_msgs || !g_acc || !scratch)
+        return fail(RN_ERR_SHAPE, "rn_depth_estimate_backward: NULL buffer");
+    const int64_t chunk = bwd_chunk(d, scratch_bytes);
+    if (chunk < 1) return fail(RN_ERR_SHAPE, "rn_depth_estimate_backward: scratch too small for one ray");
+    BwdArgs a = {};
+    a.S = S; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.acc_in = acc; a.msg_in = msgs;
+    a.g_out = g_S_new; a.g_s = g_s; a.g_msg_in = g_msgs; a.g_acc_in = g_acc; a.scratch = scratch;
+    for (int64_t first = 0; first < n_rays; first += chunk) {
+        a.first = first;
+        a.n = (n_rays - first < chunk) ? n_rays - first : chunk;
+        depth_bwd_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, S_(stream)>>>(d, a);
+        if ((rc = check_launch("depth_bwd_kernel"))) return rc;
+    }
+    return RN_OK;
+}
+
+int rn_planes_to_voxels_backward(const RnParams *p, const float *voxel_grid, const int32_t *ray_voxel_indices,
+                                 const int32_t *ray_voxel_count, const float *starts, const float *ends,
+                                 const float *S_planes, const float *g_in, int32_t g_is_wrt_S_voxel_space,
+                                 float *g_S_voxel_space, float *g_S_planes, float *g_scores, int64_t n_rays, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    if (d.D < 2 || d.D > 128) return fail(RN_ERR_UNSUPPORTED, "depth_planes must be in [2, 128]");
+    if (n_rays <= 0) return RN_OK;
+    if (!voxel_grid || !starts || !ends || !S_planes || !g_in || !g_S_planes)
+        return fail(RN_ERR_SHAPE, "rn_planes_to_voxels_backward: NULL buffer");
+    float *axes = nullptr;
+    rc = axes_from_voxel_grid(d, voxel_grid, &axes, S_(stream));
+    if (rc) return rc;
+    FrontBwdArgs a = {};
+    a.axes = axes; a.idx = ray_voxel_indices; a.count = ray_voxel_count; a.starts = starts; a.ends = ends;
+    a.S_planes = S_planes; a.g_s_norm = g_in; a.g_is_raw = g_is_wrt_S_voxel_space ? 1 : 0;
+    a.g_S_vox = g_S_voxel_space; a.g_S = g_S_planes; a.g_scores = g_scores;
+    a.n = n_rays;
+    frontend_bwd_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, S_(stream)>>>(d, a);
+    rc = check_launch("frontend_bwd_kernel");
+    scratch_free(axes, S_(stream));
+    return rc;
+}
+
+int rn_clip_renorm_backward(const RnParams *p, const float *S, const int32_t *ray_voxel_count, const float *g_s_norm,
+                            float *g_S, int64_t n_rays, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    if (n_rays <= 0) return RN_OK;
+    clip_renorm_bwd_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, S_(stream)>>>(d, S, ray_voxel_count, g_s_norm, g_S, n_rays);
+    return check_launch("clip_renorm_bwd_kernel");
+}
+
+int rn_depth_loss(const RnParams *p, int32_t kind, const float *y_true, const float *y_pred,
+                  const int32_t *ray_voxel_indices, const float *voxel_grid, const float *camera_centres, float *loss,
+                  float *g_pred, float scale, int64_t n_rays, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, false);
+    if (rc) return rc;
+    if (kind < 0 || kind > 2) return fail(RN_ERR_UNSUPPORTED, "rn_depth_loss: kind must be 0 (emd), 1 (squared_emd) or 2 (expected error)");
+    if (n_rays <= 0) return RN_OK;
+    if (!y_true || !y_pred || !loss || !g_pred) return fail(RN_ERR_SHAPE, "rn_depth_loss: NULL buffer");
+    LossArgs a = {};
+    a.y_true = y_true; a.y_pred = y_pred; a.loss = loss; a.g_pred = g_pred; a.scale = scale; a.kind = kind; a.n = n_rays;
+    float *axes = nullptr;
+    if (kind == 2) {
+        if (!ray_voxel_indices || !voxel_grid || !camera_centres) return fail(RN_ERR_SHAPE, "rn_depth_loss: kind 2 needs voxel lists, voxel_grid and camera centres");
+        rc = axes_from_voxel_grid(d, voxel_grid, &axes, S_(stream));
+        if (rc) return rc;
+        a.idx = ray_voxel_indices; a.axes = axes; a.centres = camera_centres;
+    }
+    depth_loss_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, S_(stream)>>>(d, a);
+    rc = check_launch("depth_loss_kernel");
+    scratch_free(axes, S_(stream));
+    return rc;
 }
 
 }  // extern "C"

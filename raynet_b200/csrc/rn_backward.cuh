@@ -186,7 +186,8 @@ struct FrontBwdArgs {
     const int32_t *idx, *count;
     const float *starts, *ends;   // [n][3]
     const float *S_planes;     // [n][D] the softmax output the forward pass interpolated
-    const float *g_s_norm;     // [n][M] gradient w.r.t. S_norm
+    const float *g_s_norm;     // [n][M] gradient w.r.t. S_norm (or w.r.t. S_voxel_space when g_is_raw)
+    int g_is_raw;              // 1: the incoming gradient is already w.r.t. S_voxel_space (clip_and_renorm adjoint done)
     float *g_S_vox;            // [n][M] optional out: gradient w.r.t. S_voxel_space
     float *g_S;                // [n][D] out: gradient w.r.t. S_planes
     float *g_scores;           // [n][D] optional out: gradient w.r.t. the softmax input
@@ -233,8 +234,8 @@ __global__ void __launch_bounds__(128) frontend_bwd_kernel(RnDev p, FrontBwdArgs
                 const double cl = fmin(fmax(sv, 1e-5), 1 - 1e-5);
                 if (pass == 1) { Zc += cl; dot_n += (double)gn[i] * cl; continue; }
                 // pass 2: S_norm_i = cl_i / Zc;  dot_n / Zc = sum_j gn_j S_norm_j
-                const double gcl = ((double)gn[i] - dot_n / (Zc * Zc) * Zc) / Zc;
-                const double gsv = (sv > 1e-5 && sv < 1 - 1e-5) ? gcl : 0.0;
+                const double gcl = ((double)gn[i] - dot_n / Zc) / Zc;
+                const double gsv = a.g_is_raw ? (double)gn[i] : ((sv > 1e-5 && sv < 1 - 1e-5) ? gcl : 0.0);
                 if (a.g_S_vox) a.g_S_vox[r * (int64_t)p.M + i] = (float)gsv;
                 dot_v += gsv * sv;
                 // gu_i = (gsv_i - sum_j gsv_j sv_j) / Zu needs the complete dot_v: accumulate the two parts

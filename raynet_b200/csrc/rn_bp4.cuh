@@ -67,9 +67,10 @@ __device__ __forceinline__ void rn_cp_async_wait() { asm volatile("cp.async.wait
 
 // warps per CTA of a length class: the double-buffered rows of one warp take 24 * NCH * 128 bytes
 __host__ __device__ constexpr int rn_bp4_warps(int nch) { return nch <= 6 ? 4 : 2; }
-// shared memory words of one warp: 2 x (lin, s_hat) [+ 2 x msgs unless first sweep] rows of NCH * 128
-// words + 128 words of transposition scratch
-__host__ __device__ constexpr int rn_bp4_warp_words(int nch, bool first) { return nch * RN_CHUNK * (first ? 4 : 6) + RN_CHUNK; }
+// shared memory words of one warp: 2 x (lin, s_hat) [+ 2 x msgs unless first sweep] rows of NCH * 128 words.
+// The transposition scratch of chunk c is the 128 words of the CURRENT ray's s_hat chunk c, dead once its
+// four values per lane have been read.
+__host__ __device__ constexpr int rn_bp4_warp_words(int nch, bool first) { return nch * RN_CHUNK * (first ? 4 : 6); }
 
 template <int NCH, bool kFirst>
 __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp2Args a) {
@@ -80,8 +81,7 @@ __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp
     __shared__ __align__(8) uint64_t bars[WARPS][2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float *base = reinterpret_cast<float *>(rn_bp4_smem) + (size_t)wid * rn_bp4_warp_words(NCH, kFirst);
-    // layout: lin[2][ROW], s_hat[2][ROW], (msgs[2][ROW],) scratch[128]
-    float *sX = base + (kFirst ? 4 : 6) * ROW;
+    // layout: lin[2][ROW], s_hat[2][ROW], (msgs[2][ROW])
     const uint64_t pol_stream = rn_policy_evict_first();
     const uint64_t pol_keep = rn_policy_evict_last();
 
@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp
         const int b = t & 1;
         const int64_t r = r_cur;
         const int L = L_cur;
-        __syncwarp();   // every lane is done with the buffers of ray t - 1
+        // every lane is done with the buffers of ray t - 1; its generic-proxy stores into them (transposition
+        // scratch) are ordered before the async-proxy writes of the next bulk copy
+        if (kTma) rn_fence_async_smem();
+        __syncwarp();
         if (t + 1 < nmine) {
             prefetch(r_nxt, L_nxt, b ^ 1);
             r_cur = r_nxt; L_cur = L_nxt;
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp
             __syncwarp();   // ... and every lane's copies of ray t have landed
         }
         const int *sLin = reinterpret_cast<const int *>(base + b * ROW);
-        const float *sS = base + (2 + b) * ROW;
+        float *sS = base + (2 + b) * ROW;
         const float *sM = base + (4 + b) * ROW;   // !kFirst only
         float *m_row = a.msgs + r * (int64_t)p.row_stride;
 
@@ -206,7 +209,8 @@ __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp
             if (uniform) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) accv[j] = ga[c][j];
-            } else {   // lane-consecutive -> 4 consecutive voxels per lane
+            } else {   // lane-consecutive -> 4 consecutive voxels per lane, through the s_hat chunk just read
+                float *sX = sS + c * RN_CHUNK;
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 4; j++) sX[32 * j + lane] = ga[c][j];
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp
             const int i0 = c * RN_CHUNK + 4 * lane;
             const float4 msg4 = make_float4(msg[0], msg[1], msg[2], msg[3]);
             if (c < NCH - 1 || i0 < L) rn_st_stream4_pol(m_row + i0, msg4, pol_stream);   // rows hold whole quads
-            __syncwarp();
+            float *sX = sS + c * RN_CHUNK;   // every chunk has its own scratch: no wait for the previous chunk's readers
             *reinterpret_cast<float4 *>(sX + 4 * lane) = msg4;
             __syncwarp();
 #pragma unroll

@@ -285,3 +285,54 @@ def test_pointcloud_oracle_vs_reference_execution(borders, thr, nn):
     assert plain.shape == g["plain_" + key].shape and np.abs(plain - g["plain_" + key]).max() < 1e-12
     cons = pointcloud_np.fuse(g["depth"], g["gt"], g["P"], g["P_pinv"], g["centre"], borders, thr, nn)
     assert cons.shape == g["cons_" + key].shape and np.abs(cons - g["cons_" + key]).max() < 1e-12
+
+
+# ----------------------------------------------------------------------------- the autograd oracle
+def _training_case(oracle, n_rays=120, seed=3):
+    from rig import Case
+    c = Case(24, 2, 8, 32, 32, 72, n_rays=n_rays, seed=seed)
+    o = oracle.frontend(c.ray_idxs, c.features, c.P, c.P_inv, c.centre, c.vgrid, c.bbox, c.grid, c.M, c.D, c.V, 32,
+                        c.H, c.W, 11, want_stages=True)
+    rng = np.random.RandomState(seed)
+    scores = rng.randn(c.N, c.D) * 2.0
+    target = np.zeros((c.N, c.M), np.float32)
+    for r in range(c.N):
+        L = int(o["cnt"][r])
+        if L > 0:
+            t = rng.rand(L) ** 4
+            target[r, :L] = t / t.sum()
+    return c, o, scores, target
+
+
+def test_autograd_restatement_reproduces_the_c_oracle(oracle):
+    """oracle/bp_autograd.py (float64 torch restatement of mrf_tf.py + the plane->voxel interpolation) must
+    reproduce rn_oracle.c's forward pass -- that is what pins the reference gradients used by the GPU tests."""
+    import torch
+    from oracle import bp_autograd as ag
+    c, o, scores, target = _training_case(oracle)
+    S = torch.softmax(torch.from_numpy(scores), dim=1)
+    starts, ends = o["starts"], o["ends"]
+    S32 = S.numpy().astype(np.float32)
+    S_vox_c = oracle.planes_voxels_mapping(c.vgrid, c.grid, o["idx"], o["cnt"], starts, ends, S32, c.M)
+    acc_c, msgs_c = oracle.belief_propagation(S_vox_c, o["idx"], o["cnt"], c.grid, gamma=0.05, bp_iterations=3, acc_f64=True)
+    Smrf_c = oracle.depth_distribution(S_vox_c, o["idx"], o["cnt"], c.grid, acc_c, msgs_c, acc_f64=True)
+    loss, S_mrf, S_vox = ag.forward_graph(torch.from_numpy(scores), o["idx"], o["cnt"], c.grid, c.vgrid, starts, ends,
+                                          np.tile(np.append(c.centre[:3], 1.0), (c.N, 1)), target,
+                                          torch.tensor(0.05, dtype=torch.float64), 3, "squared_emd")
+    assert np.abs(S_vox.numpy() - S_vox_c).max() <= 2e-6
+    assert np.abs(S_mrf.numpy() - Smrf_c).max() <= 1e-5
+    assert np.isfinite(float(loss))
+
+
+def test_autograd_restatement_gradcheck(oracle):
+    """float64 finite differences of the restatement itself (torch.autograd.gradcheck) on a tiny problem."""
+    import torch
+    from oracle import bp_autograd as ag
+    c, o, scores, target = _training_case(oracle, n_rays=6, seed=5)
+    cam = np.tile(np.append(c.centre[:3], 1.0), (c.N, 1))
+    for loss in ("squared_emd", "expected_squared_error"):
+        def f(z, g):
+            return ag.forward_graph(z, o["idx"], o["cnt"], c.grid, c.vgrid, o["starts"], o["ends"], cam, target, g, 2, loss)[0]
+        z = torch.from_numpy(scores).requires_grad_(True)
+        g = torch.tensor(0.05, dtype=torch.float64, requires_grad=True)
+        assert torch.autograd.gradcheck(f, (z, g), eps=1e-6, atol=1e-7, rtol=1e-4)

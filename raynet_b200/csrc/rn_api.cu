@@ -94,7 +94,7 @@ struct SmemOptIn {
     size_t configured[64] = {};
     template <typename K>
     int ensure(K kernel, size_t smem, const char *what) {
-        if (smem <= 48 * 1024) return RN_OK;
+        if (smem + 2048 <= 48 * 1024) return RN_OK;   // static shared memory (mbarriers, ...) counts against the default limit too
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return fail(RN_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));

@@ -199,7 +199,8 @@ class RayNetForwardPass(ForwardPass):
     is cut into `world` contiguous blocks (sharding.image_segments), the occupancy accumulator is
     all-reduced after every sweep and every rank yields the complete depth maps.  `shard="images"` --
     `images_range` selects THIS rank's reference images (rank, n, world), only the accumulator is
-    shared and a rank yields its own images' maps.
+    shared and a rank yields its own images' maps.  `shard="none"` -- ignore the process group (this process runs
+    the whole job alone).
 
     Feature hook: a `model` that has `predict_features(scene, view_indices)` is asked for the
     (n, H+p+1, W+p+1, F) float32 maps of those views directly (raynet_b200.models.SimpleCNN leaves
@@ -211,7 +212,7 @@ class RayNetForwardPass(ForwardPass):
                  bp_iterations=3, memory_budget=None, shard="rays", parity=False):
         super(RayNetForwardPass, self).__init__(model, generation_params, sampling_scheme, image_shape,
                                                 rays_batch, filter_out_rays)
-        assert shard in ("rays", "images")
+        assert shard in ("rays", "images", "none")
         self.rays_batch = rays_batch
         self.ref_idx = -1
         self.bp_iterations = bp_iterations      # hard-coded to 3 in the reference (forward_pass.py:590)
@@ -268,7 +269,7 @@ class RayNetForwardPass(ForwardPass):
                                  scene.image_shape[1], gp.padding, scene.bbox.ravel(), vg.shape[1:],
                                  gamma=gp.gamma_mrf if gp.gamma_mrf is not None else 0.05,
                                  max_rays=n_rays_total, parity=self.parity, memory_budget=self.memory_budget,
-                                 max_segment_rays=max_segment)
+                                 max_segment_rays=max_segment, use_distributed=None if self.shard != "none" else False)
         eng.set_voxel_grid(vg)
         return eng
 
@@ -314,7 +315,7 @@ class RayNetForwardPass(ForwardPass):
         H, W = scene.image_shape
         dev = device()
         dist = torch.distributed
-        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized() and self.shard != "none") else 1
         rank = dist.get_rank() if world > 1 else 0
         by_rays = world > 1 and self.shard == "rays"
         img_ids = list(range(start_img_idx, end_img_idx, skip))

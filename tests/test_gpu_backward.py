@@ -28,7 +28,7 @@ def _gpu_run(torch, c, o, scores, target, loss, iters, gamma=0.05):
     L, S_mrf = forward_backward_pass(z, d(c.vgrid), d(o["idx"]), d(o["cnt"]), d(target), d(o["starts"]), d(o["ends"]),
                                      d(cam), c.grid, gamma=g, bp_iterations=iters, loss=loss)
     L.backward()
-    return float(L), S_mrf.detach().cpu().numpy(), z.grad.cpu().numpy(), float(g.grad)
+    return float(L.detach()), S_mrf.detach().cpu().numpy(), z.grad.cpu().numpy(), float(g.grad)
 
 
 @pytest.mark.parametrize("loss", ["squared_emd", "emd", "expected_squared_error"])
@@ -54,8 +54,8 @@ def test_backward_matches_autograd_of_the_reference_graph(torch_cuda, oracle, lo
         "grad_scores_rel_to_max": e_gz, "grad_gamma_rel": e_gg, "max_abs_grad_scores": scale}
     assert e_fwd <= 1e-5
     assert abs(L - float(L_ref)) <= 1e-4 * abs(float(L_ref))
-    assert e_gz <= 2e-3, e_gz           # float32 forward checkpoints, float32 gradient atomics
-    assert e_gg <= 1e-2, (gg, gg_ref)
+    assert e_gz <= 2e-5, e_gz           # measured 4e-7 .. 6e-7 (profiles/r02_parity.json): float32 checkpoints and atomics
+    assert e_gg <= 2e-5, (gg, gg_ref)
     # direction: the cosine between the two gradients
     cos = float((gz * gz_ref).sum() / (np.linalg.norm(gz) * np.linalg.norm(gz_ref)))
     assert cos > 1 - 1e-5

@@ -233,3 +233,34 @@ def test_restrepo_scene_on_disk(tmp_path):
             c = r.get_image(i).camera
             assert np.array_equal(c.K, g["K"][i]) and np.array_equal(c.R, g["R"][i]) and np.array_equal(c.t, g["t"][i])
             assert np.array_equal(c.P, g["P"][i]) and np.array_equal(c.center, g["center"][i])
+
+
+def test_dtu_scene_on_disk(tmp_path):
+    """A scene written in the DTU MVS layout (tests/golden/make_dtu_golden.py holds the writer and the inputs)
+    reads back to what the reference's own DTUScene methods produced on it: K / R / t per view, the bounding
+    box from the ObsMask file, ground-truth distance maps, per-pixel depths; view 50 and the other illumination
+    settings are ignored."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_dtu_golden import write_scene
+    from raynet_b200.common.scene import DTUScene
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dtu_golden.npz"))
+    write_scene(str(tmp_path), 7, g["K_in"], list(g["P_in"]), g["pix"], g["depths"], g["bb"])
+    s = DTUScene(str(tmp_path), 7)
+    n = g["P_in"].shape[0]
+    assert s.n_images == n and s.image_shape == tuple(g["pix"].shape[1:3])
+    assert np.array_equal(s.bbox, g["bbox"]) and s.bbox.dtype == np.float32
+    assert s.observation_mask.shape == (2, 2, 2)
+    for i in range(n):
+        im = s.get_image(i)
+        assert np.array_equal(im.camera.K, g["K"][i])
+        assert np.allclose(im.camera.R, g["R"][i], rtol=0, atol=1e-6) and np.allclose(im.camera.t, g["t"][i], rtol=1e-6)
+        assert np.allclose(im.camera.center, g["center"][i], rtol=1e-5, atol=1e-3)
+        assert np.array_equal(im.image, g["pix"][i].astype(np.float32) / np.float32(255.))
+        assert np.allclose(s.get_depth_map(i), g["depth_maps"][i], rtol=1e-5, atol=1e-3)
+    for (i, y, x), want in zip(g["pixel_queries"], g["pixel_depths"]):
+        got = s.get_depth_for_pixel(int(i), int(y), int(x))
+        assert (got is None and np.isnan(want)) or abs(got - want) <= 1e-3
+    assert s.view_order(1, neighbors=2) == [1, 0, 2]
+    assert len(s.get_image_with_neighbors(1, neighbors=2)) == 3
+    with pytest.raises(NotImplementedError):
+        s.get_pointcloud()

@@ -4,14 +4,17 @@
 //   bp2_kernel  rows staged by TMA bulk copies, per-voxel state in shared memory        5.25
 //   (bp3)       state in registers per length class, rows loaded straight to registers  4.70
 //   bp4 round 1 bp3 + the NEXT ray's rows prefetched into shared memory by cp.async     3.73
+//   bp4 round 2 rows staged by TMA (one elected lane, three cp.async.bulk per ray, mbarrier)   4.15
+//               the same with the per-lane cp.async staging                               3.78
 // ncu on the round-1 version: L1TEX data pipe 75 % busy, 3 * NCH LDGSTS per lane per ray for the row
-// staging on top of the gathers, the REDs and the transposition traffic.  This version stages the rows
-// with ONE elected lane issuing three cp.async.bulk copies per ray (TMA, UBLKCP: no LSU / L1TEX
-// involvement, completion on an mbarrier), keeps the transposition between the lane-consecutive gather /
-// RED layout and the 4-voxels-per-lane scan layout in a scratch of its own (no generic store ever
-// touches bytes the async proxy writes), and is instantiated for every length class up to
-// RN_MAX_NCH = 12 chunks (1536 voxels: C5), with CTAs of two warps for the long classes so that the
-// double-buffered rows of a CTA still allow several CTAs per SM.
+// staging on top of the gathers, the REDs and the transposition traffic.  Round 2 built the TMA staging
+// the north star asks for (RN_BP4_TMA=1: UBLKCP, no LSU / L1TEX involvement, completion on an mbarrier,
+// proxy fence before a buffer is handed back to the async proxy) and measured it SLOWER than the per-lane
+// copies -- rows of ~1.3 KB are too small for one bulk operation each -- so it is a build option, not the
+// default.  The kernel is instantiated for every length class up to RN_MAX_NCH = 12 chunks (1536 voxels:
+// C5), with CTAs of two warps for the long classes so that the double-buffered rows of a CTA still allow
+// several CTAs per SM; the transposition between the lane-consecutive gather / RED layout and the
+// 4-voxels-per-lane scan layout goes through the s_hat chunk that has just been consumed.
 //
 // Rays are binned by length class (rn_class_of: NCH = ceil(L / 128) chunks); the kernel is instantiated
 // per class and fully unrolled: every per-voxel quantity that has to survive from the forward to the
@@ -55,7 +58,11 @@ __device__ __forceinline__ float rn_occ_w2(float acc, float msg) {
 #define RN_BP4_WAIT_ONE 0
 #endif
 #ifndef RN_BP4_TMA
-#define RN_BP4_TMA 1      // 1: rows staged by cp.async.bulk + mbarrier (TMA); 0: by per-lane 16-byte cp.async (LDGSTS)
+// 0: rows staged by per-lane 16-byte cp.async (LDGSTS); 1: by cp.async.bulk + mbarrier (TMA, UBLKCP).
+// Measured on C3 (B200, same box, ms per non-first sweep; profiles/README.md): LDGSTS 3.78, TMA 4.15 -- a ray's
+// three rows are ~1.3 KB each, one bulk copy per row per ray (12 small bulk operations per microsecond and SM)
+// costs more than the LSU slots the per-lane copies take, so the per-lane copies are the default.
+#define RN_BP4_TMA 0
 #endif
 
 __device__ __forceinline__ void rn_cp_async16(uint32_t dst_smem, const void *src, uint64_t pol) {

@@ -34,7 +34,8 @@ class SimpleCNN(object):
         self.launches = 0
         self._scratch = None      # two device buffers for the intermediate layers
         self.last_h2d_bytes = 0   # bytes of zero-padded images uploaded by the last predict_features()
-        self._staging = None      # pinned host buffer of the zero-padded views
+        self._staging = None      # pinned host staging buffer for views whose pixels are pageable
+        self._padded = None       # device buffer of the zero-padded views (border zeroed once)
 
     # ------------------------------------------------------------------ weights
     @classmethod
@@ -124,19 +125,33 @@ class SimpleCNN(object):
 
     def predict_features(self, scene, view_indices, padding=11):
         """RayNetForwardPass hook: feature maps of the given views as ONE CUDA tensor
-        [n, H+padding+1, W+padding+1, 32] (zero-padding as forward_pass.py:181-198).  The zero-padded views
-        are assembled in a cached pinned buffer (its border stays zero) and uploaded with one DMA."""
+        [n, H+padding+1, W+padding+1, 32] (zero-padding as forward_pass.py:181-198).  The zero-padded stack
+        lives on the device (its border is zeroed once); a view whose pixel buffer is page-locked float32 is
+        uploaded straight from it (asynchronous DMA), anything else through a cached pinned staging buffer."""
         images = [scene.get_image(v).image for v in view_indices]
         H, W, C = images[0].shape
+        dev = device()
         shape = (len(images), H + 2 * padding, W + 2 * padding, C)
-        X = self._staging
-        if X is None or tuple(X.shape) != shape:
-            X = self._staging = torch.zeros(shape, dtype=torch.float32).pin_memory()
-        inner = X.numpy()[:, padding:padding + H, padding:padding + W, :]
+        X = self._padded
+        if X is None or tuple(X.shape) != shape or X.device != dev:
+            X = self._padded = torch.zeros(shape, dtype=torch.float32, device=dev)
+        bytes_up = 0
         for k, im in enumerate(images):
-            inner[k] = im
-        self.last_h2d_bytes = X.numel() * 4
-        return self.predict_device(X.to(device(), non_blocking=True))
+            src = None
+            if isinstance(im, np.ndarray) and im.dtype == np.float32 and im.flags["C_CONTIGUOUS"]:
+                t = torch.from_numpy(im)
+                if t.is_pinned():
+                    src = t
+            if src is None:
+                st = self._staging
+                if st is None or tuple(st.shape) != (len(images), H, W, C):
+                    st = self._staging = torch.empty((len(images), H, W, C), dtype=torch.float32).pin_memory()
+                st[k].numpy()[...] = im
+                src = st[k]
+            X[k, padding:padding + H, padding:padding + W, :].copy_(src, non_blocking=True)
+            bytes_up += src.numel() * 4
+        self.last_h2d_bytes = bytes_up
+        return self.predict_device(X)
 
 
 def create_simple_cnn(input_shape=(None, None, 3), seed=0):

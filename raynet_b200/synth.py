@@ -101,7 +101,7 @@ class SyntheticScene(object):
     neighbours."""
 
     def __init__(self, n_views, H, W, grid_shape, bbox=(-1, -1, -1, 1, 1, 1), neighbors=None, with_images=False,
-                 seed=0, neighbor_stride=1):
+                 seed=0, neighbor_stride=1, pinned=None):
         self.n_views = n_views
         self._H, self._W = H, W
         self.grid_shape = np.asarray(grid_shape, dtype=np.int32)
@@ -110,7 +110,21 @@ class SyntheticScene(object):
         self.neighbor_stride = int(neighbor_stride)
         cams = ring_cameras(n_views, H, W)
         rng = np.random.RandomState(seed)
-        self.images = [Image(c, rng.rand(H, W, 3).astype(np.float32) if with_images else None) for c in cams]
+        pixels = [None] * n_views
+        if with_images:
+            # the pixel buffers live in ONE block of (when a CUDA device is present) page-locked host memory,
+            # like an image cache a data loader fills: uploads from it are true asynchronous DMAs
+            import torch
+            block = torch.empty((n_views, H, W, 3), dtype=torch.float32)
+            if pinned is None:
+                pinned = torch.cuda.is_available()
+            if pinned:
+                block = block.pin_memory()
+            self._pixel_block = block
+            pixels = block.numpy()
+            for v in range(n_views):
+                pixels[v] = rng.rand(H, W, 3).astype(np.float32)
+        self.images = [Image(c, pixels[v]) for v, c in enumerate(cams)]
         self._voxel_grid = None
 
     @property

@@ -55,7 +55,7 @@ def main():
         occ_b = alone.engine.occupancy().cpu().numpy()
         out[name] = (float(same.mean()), float(np.abs(occ_a - occ_b).max()), sharded.engine.n_rays, alone.engine.n_rays)
         assert same.mean() > 0.999, (name, same.mean())
-        assert np.abs(occ_a - occ_b).max() <= 2e-6, (name, np.abs(occ_a - occ_b).max())
+        assert np.abs(occ_a - occ_b).max() <= 1e-5, (name, np.abs(occ_a - occ_b).max())
         assert sharded.engine.n_rays < alone.engine.n_rays or world == 1
         # every rank holds the same complete maps
         t = torch.from_numpy(a).cuda()
@@ -92,4 +92,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+        print("MULTI_GPU_CHECK failed on rank %s\n%s" % (os.environ.get("RANK"), traceback.format_exc()), flush=True)
+        raise

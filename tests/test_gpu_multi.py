@@ -18,4 +18,6 @@ def test_ray_sharded_forward_pass_on_two_gpus():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", port, os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0 and "MULTI_GPU_CHECK ok" in r.stdout, r.stdout[-3000:]
+    if r.returncode != 0 or "MULTI_GPU_CHECK ok" not in r.stdout:
+        k = r.stdout.find("MULTI_GPU_CHECK failed")
+        pytest.fail(r.stdout[k:k + 4000] if k >= 0 else r.stdout[-4000:])

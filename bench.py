@@ -412,7 +412,8 @@ def run_gpu_arm(args, cfg):
     dev = torch.device("cuda", local)
 
     # ---------------- device-resident arm -------------------------------------------------------
-    eng = RayPotentialEngine(M, D, V, F, H, W, PADDING, scene.bbox.ravel(), (G, G, G), gamma=GAMMA, max_rays=n_rays)
+    eng = RayPotentialEngine(M, D, V, F, H, W, PADDING, scene.bbox.ravel(), (G, G, G), gamma=GAMMA, max_rays=n_rays,
+                             collective=args.collective)
     eng.set_voxel_grid(scene.voxel_grid())
     feats = model.host.to(dev)
     slot = dict((v, k) for k, v in enumerate(my_views))
@@ -488,6 +489,7 @@ def run_gpu_arm(args, cfg):
     total_rays = int(totals.item())
     value = total_rays / (ms_step * 1e-3)
 
+    collective = eng.collective
     e2e = None
     del eng, feats, model
     torch.cuda.empty_cache()
@@ -536,7 +538,10 @@ def run_gpu_arm(args, cfg):
                 "mean_voxels_per_ray": mean_L, "longest_ray": max_L,
                 "parallelism": "rays sharded in %d contiguous blocks of the (image, pixel) enumeration" % world
                                if scaling == "strong" else "whole reference images per rank, dp%d" % world,
-                "collective": ("all-reduce f32[%d^3] per sweep (NCCL)" % G) if world > 1 else "none",
+                "collective": ("sum of the per-rank partial f32[%d^3] accumulators after every sweep: %s" % (G, {
+                    "peer": "this library's fused barrier + reduce + broadcast kernel over NVLink peer memory "
+                            "(rn_peer_allreduce_f32)"}.get(collective, "torch.distributed all_reduce, " + collective)))
+                              if world > 1 else "none",
                 "l2": "per-step working set (%.1f GB of per-ray state on rank 0) is far larger than L2; no flush needed"
                       % (3 * n_rays * M * 4 / 1e9),
             },
@@ -595,6 +600,8 @@ def main():
                     help="strong: the fixed job sharded by rays over the GPUs (default); weak: fixed work per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs only)")
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
+                    help="exchange step of the multi-GPU path (engine.py); auto = peer kernel when the GPUs map each other")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

@@ -370,6 +370,20 @@ int rn_depth_loss(const RnParams *p, int32_t kind, const float *y_true, const fl
                   const int32_t *ray_voxel_indices, const float *voxel_grid, const float *camera_centres, float *loss,
                   float *g_pred, float scale, int64_t n_rays, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * The exchange step of the multi-GPU path as one kernel over NVLink peer memory: every rank
+ * calls it on its own stream after its sweep; result[p][i] = prior + sum_q partial[q][i] lands in EVERY rank's
+ * result buffer (slice `rank` of the grid is reduced and broadcast by this rank).  peer_partials / peer_results
+ * / peer_flags: HOST arrays of `world` device addresses -- the same buffer as mapped from every rank (peer
+ * mappings, e.g. torch.distributed._symmetric_memory); flags: uint32 [n_ctas][world] per rank, zeroed once;
+ * epoch: 2 x the number of earlier calls on these flags (the same on all ranks); n_ctas <= SM count (all CTAs
+ * of all ranks must be resident: a CTA waits for its twin on every peer); n: float32 elements, multiple of 4.
+ * Replaces ncclAllReduce + the prior epilogue; the reference has no multi-GPU code.
+ * ------------------------------------------------------------------------------------- */
+int rn_peer_allreduce_f32(const uint64_t *peer_partials, const uint64_t *peer_results, const uint64_t *peer_flags,
+                          int32_t rank, int32_t world, int32_t n_ctas, uint32_t epoch, float prior, int64_t n,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

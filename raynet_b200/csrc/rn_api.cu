@@ -9,6 +9,7 @@
 #include "rn_bp4.cuh"
 #include "rn_parity.cuh"
 #include "rn_backward.cuh"
+#include "rn_peer.cuh"
 #include "rn_simmap3.cuh"
 #include "rn_cnn.cuh"
 #include "rn_fusion.cuh"
@@ -984,6 +985,31 @@ int rn_depth_loss(const RnParams *p, int32_t kind, const float *y_true, const fl
     rc = check_launch("depth_loss_kernel");
     scratch_free(axes, S_(stream));
     return rc;
+}
+
+// ---- the exchange step over NVLink peer memory (rn_peer.cuh) ----------------------------------------------------
+int rn_peer_allreduce_f32(const uint64_t *peer_partials, const uint64_t *peer_results, const uint64_t *peer_flags,
+                          int32_t rank, int32_t world, int32_t n_ctas, uint32_t epoch, float prior, int64_t n,
+                          void *stream) {
+    if (world < 1 || world > RN_PEER_MAX_WORLD || rank < 0 || rank >= world)
+        return fail(RN_ERR_UNSUPPORTED, "rn_peer_allreduce_f32: world size must be in [1, %d]", RN_PEER_MAX_WORLD);
+    if (!peer_partials || !peer_results || !peer_flags) return fail(RN_ERR_SHAPE, "rn_peer_allreduce_f32: NULL pointer table");
+    if (n <= 0 || (n & 3)) return fail(RN_ERR_SHAPE, "rn_peer_allreduce_f32: n must be a positive multiple of 4");
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail(RN_ERR_CUDA, "rn_peer_allreduce_f32: %s", cudaGetErrorString(e));
+    if (n_ctas < 1 || n_ctas > sms) return fail(RN_ERR_SHAPE, "rn_peer_allreduce_f32: n_ctas must be in [1, %d] (all CTAs must be resident)", sms);
+    PeerArgs a = {};
+    for (int p = 0; p < world; p++) {
+        a.partial[p] = reinterpret_cast<const float *>(peer_partials[p]);
+        a.result[p] = reinterpret_cast<float *>(peer_results[p]);
+        a.flags[p] = reinterpret_cast<uint32_t *>(peer_flags[p]);
+        if (!a.partial[p] || !a.result[p] || !a.flags[p]) return fail(RN_ERR_SHAPE, "rn_peer_allreduce_f32: NULL peer pointer");
+    }
+    a.rank = rank; a.world = world; a.epoch = epoch; a.prior = prior; a.n = n;
+    peer_allreduce_kernel<<<(unsigned)n_ctas, 512, 0, S(stream)>>>(a);
+    return check_launch("peer_allreduce_kernel");
 }
 
 }  // extern "C"

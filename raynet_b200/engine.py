@@ -62,12 +62,16 @@ class _Group(object):
 class RayPotentialEngine(object):
     def __init__(self, M, D, n_views, F, H, W, padding, bbox, grid_shape, gamma=0.05, max_rays=0,
                  process_group=None, use_distributed=None, parity=False, memory_budget=None,
-                 max_segment_rays=None):
+                 max_segment_rays=None, collective="auto"):
         """M, D, n_views, F, H, W, padding, bbox, grid_shape: as perform_raynet_fp
         (raynet_fp.py:10-41).  Rows of the per-ray state are padded to rn_row_stride(M) floats.
         max_rays: capacity of the per-ray state on this rank.  memory_budget: bytes of HBM the
         per-ray state may take (default: 85 % of the free memory at construction).
-        max_segment_rays: upper bound on the rays of one segment (default H * W)."""
+        max_segment_rays: upper bound on the rays of one segment (default H * W).
+        collective: how the per-rank partial accumulators are summed after a sweep when world > 1 --
+        "peer": this library's fused exchange kernel over NVLink peer memory (sharding.PeerExchange),
+        "nccl": torch.distributed all_reduce, "auto": peer when the GPUs can map each other's memory
+        (float32 accumulators only), else nccl; self.collective says which one runs."""
         M = int(M)
         self.M, self.D, self.V, self.F, self.H, self.W, self.padding = M, D, n_views, F, H, W, padding
         self.grid_shape = tuple(int(g) for g in np.asarray(grid_shape).ravel())
@@ -111,9 +115,27 @@ class RayPotentialEngine(object):
         self.lin = torch.empty((rows, self.R), dtype=torch.int32, **kw)
         self.s_hat = torch.empty((rows, self.R), dtype=torch.float32, **kw)
         acc_dtype = torch.float64 if self.parity else torch.float32
-        self.acc_prev = torch.full((self.GB,), self.prior, dtype=acc_dtype, **kw)
+        self.collective = "none"
+        self._peer = None
+        if self.world > 1:
+            assert collective in ("auto", "peer", "nccl")
+            self.collective = "nccl"
+            if collective in ("auto", "peer") and not self.parity:
+                try:
+                    self._peer = sharding.PeerExchange(self.GB, self.dev, self.pg)
+                    self.collective = "peer"
+                except RuntimeError as e:
+                    if collective == "peer":
+                        raise
+                    self.collective = "nccl (%s)" % (e,)
+        if self._peer is not None:
+            # fixed roles: sweeps read `result` and scatter-add into `partial`; the exchange kernel refills `result`
+            self.acc_prev, self.acc_new = self._peer.result, self._peer.partial
+            self.acc_prev.fill_(self.prior)
+        else:
+            self.acc_prev = torch.full((self.GB,), self.prior, dtype=acc_dtype, **kw)
+            self.acc_new = torch.empty((self.GB,), dtype=acc_dtype, **kw)
         self._acc_uniform = True         # acc_prev holds the prior everywhere (until a sweep or set_accumulator)
-        self.acc_new = torch.empty((self.GB,), dtype=acc_dtype, **kw)
         self.axes = torch.zeros((sum(self.grid_shape),), dtype=torch.float32, **kw)
         self._planes = None              # float32 [max_segment_rays, D] plane-distribution scratch of the front end
         self._side = None                # side stream + pinned buffer for the class-size read-back
@@ -357,7 +379,7 @@ class RayPotentialEngine(object):
         if not self._classes_ready:
             self._resolve_classes()
         st = current_stream_ptr()
-        self._fill(self.acc_new, sharding.seed_value(self.rank, self.prior))
+        self._fill(self.acc_new, 0.0 if self._peer is not None else sharding.seed_value(self.rank, self.prior))
         if self.sweep_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
@@ -380,9 +402,13 @@ class RayPotentialEngine(object):
         if self.sweep_events is not None:
             ev[1].record()
             self.sweep_events.append(ev)
-        if self.world > 1:
-            sharding.allreduce_accumulator(self.acc_new, self.pg)
-        self.acc_prev, self.acc_new = self.acc_new, self.acc_prev
+        if self._peer is not None:
+            self._peer.allreduce(self.prior)          # acc_prev (= the peer-mapped result buffer) <- prior + sum of partials
+            self.launches += 1
+        else:
+            if self.world > 1:
+                sharding.allreduce_accumulator(self.acc_new, self.pg)
+            self.acc_prev, self.acc_new = self.acc_new, self.acc_prev
         self.iterations_done += 1
 
     def run_bp(self, iterations):

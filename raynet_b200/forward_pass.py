@@ -209,7 +209,7 @@ class RayNetForwardPass(ForwardPass):
     share and the maps are exchanged with one all-gather over NVLink."""
 
     def __init__(self, model, generation_params, sampling_scheme, image_shape, rays_batch, filter_out_rays=False,
-                 bp_iterations=3, memory_budget=None, shard="rays", parity=False):
+                 bp_iterations=3, memory_budget=None, shard="rays", parity=False, collective="auto"):
         super(RayNetForwardPass, self).__init__(model, generation_params, sampling_scheme, image_shape,
                                                 rays_batch, filter_out_rays)
         assert shard in ("rays", "images", "none")
@@ -219,6 +219,7 @@ class RayNetForwardPass(ForwardPass):
         self.memory_budget = memory_budget
         self.shard = shard
         self.parity = parity
+        self.collective = collective            # exchange step of the multi-GPU path: "auto", "peer" or "nccl" (engine.py)
         self.engine = None
         self._de = None
         self._feat_dev = None
@@ -269,7 +270,8 @@ class RayNetForwardPass(ForwardPass):
                                  scene.image_shape[1], gp.padding, scene.bbox.ravel(), vg.shape[1:],
                                  gamma=gp.gamma_mrf if gp.gamma_mrf is not None else 0.05,
                                  max_rays=n_rays_total, parity=self.parity, memory_budget=self.memory_budget,
-                                 max_segment_rays=max_segment, use_distributed=None if self.shard != "none" else False)
+                                 max_segment_rays=max_segment, use_distributed=None if self.shard != "none" else False,
+                                 collective=self.collective)
         eng.set_voxel_grid(vg)
         return eng
 

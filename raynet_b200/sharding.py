@@ -12,8 +12,14 @@ the per-rank partial accumulators are summed once per sweep.
     prior + sum of all messages -- no epilogue pass over the grid;
   * `allreduce_accumulator` is the one collective of the path.
 
+  * `PeerExchange` replaces that NCCL call on NVLink-connected GPUs by ONE kernel of this library over
+    peer-mapped buffers (csrc/rn_peer.cuh): barrier, reduce + broadcast of one slice per rank, barrier, prior
+    fused in.  torch.distributed._symmetric_memory only provides the peer mappings.
+
 This module is what the world_size-2 gloo tests exercise on CPU.
 """
+import ctypes
+
 import torch
 
 
@@ -75,3 +81,45 @@ def allreduce_accumulator(acc, group=None):
         if torch.distributed.get_world_size(group) > 1:
             torch.distributed.all_reduce(acc, op=torch.distributed.ReduceOp.SUM, group=group)
     return acc
+
+
+class PeerExchange(object):
+    """Peer-mapped partial / result accumulators of one rank + the fused exchange kernel.
+
+        ex = PeerExchange(n_elements, device, group)      # collective: every rank of the group constructs it
+        ex.partial   float32 [n]   this rank's sweep scatter-adds into it (zero it before every sweep)
+        ex.result    float32 [n]   after ex.allreduce(prior): prior + sum over ranks of partial, on every rank
+    Raises RuntimeError when the GPUs cannot map each other's memory (the caller then stays on NCCL)."""
+
+    def __init__(self, n, device, group=None, n_ctas=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        from .cuda_implementations.utils import current_stream_ptr
+        self._lib, self._stream = _lib, current_stream_ptr
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n = int(n)
+        assert self.n % 4 == 0
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        self.n_ctas = int(n_ctas or sms)
+        try:
+            self.partial = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+            self.result = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+            self.flags = symm_mem.empty(self.n_ctas * self.world, dtype=torch.int32, device=device)
+            self.flags.zero_()
+            handles = [symm_mem.rendezvous(t, group.group_name) for t in (self.partial, self.result, self.flags)]
+        except Exception as e:      # no NVLink / P2P mapping between these devices
+            raise RuntimeError("peer-mapped accumulators unavailable: %r" % (e,))
+        self._handles = handles     # keep the mappings alive
+        self._tables = [(ctypes.c_uint64 * self.world)(*[int(p) for p in h.buffer_ptrs]) for h in handles]
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)         # every rank's flags are zeroed before anyone signals
+
+    def allreduce(self, prior):
+        self._lib.call("rn_peer_allreduce_f32", self._tables[0], self._tables[1], self._tables[2], self.rank, self.world,
+                       self.n_ctas, ctypes.c_uint32(self.epoch & 0xffffffff), float(prior), self.n, self._stream())
+        self.epoch += 2
+        return self.result

@@ -43,8 +43,10 @@ def main():
     gp = GenerationParameters(depth_planes=D, neighbors=V - 1, grid_shape=np.array([G, G, G], np.int32),
                               max_number_of_marched_voxels=M, padding=11, gamma_mrf=0.05)
     out = {}
-    for name, model in (("features", FeatureModel()), ("cnn", SimpleCNN.random_init(channels=3, seed=1))):
-        sharded = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, H * W, bp_iterations=I, shard="rays")
+    for name, model, coll in (("features", FeatureModel(), "auto"), ("features_nccl", FeatureModel(), "nccl"),
+                              ("cnn", SimpleCNN.random_init(channels=3, seed=1), "auto")):
+        sharded = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, H * W, bp_iterations=I, shard="rays",
+                                    collective=coll)
         alone = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, H * W, bp_iterations=I, shard="none")
         a = np.stack(list(sharded.forward_pass(scene, (0, V, 1))))
         b = np.stack(list(alone.forward_pass(scene, (0, V, 1))))
@@ -53,12 +55,17 @@ def main():
         same = np.abs(a - b) < 1e-6
         occ_a = sharded.engine.occupancy().cpu().numpy()
         occ_b = alone.engine.occupancy().cpu().numpy()
-        out[name] = (float(same.mean()), float(np.abs(occ_a - occ_b).max()), sharded.engine.n_rays, alone.engine.n_rays)
+        out[name] = (float(same.mean()), float(np.abs(occ_a - occ_b).max()), sharded.engine.n_rays, alone.engine.n_rays,
+                     sharded.engine.collective)
+        # twice more on the same engine: the flags / epochs of the exchange kernel carry over between calls
+        for _ in range(2):
+            a2 = np.stack(list(sharded.forward_pass(scene, (0, V, 1))))
+            assert (np.abs(a2 - b) < 1e-6).mean() > 0.999
         assert same.mean() > 0.999, (name, same.mean())
         assert np.abs(occ_a - occ_b).max() <= 1e-5, (name, np.abs(occ_a - occ_b).max())
         assert sharded.engine.n_rays < alone.engine.n_rays or world == 1
         # every rank holds the same complete maps
-        t = torch.from_numpy(a).cuda()
+        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
         lo, hi = t.clone(), t.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)

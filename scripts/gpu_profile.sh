@@ -6,7 +6,7 @@
 #   3. --set full of the dominant kernels: bp4_kernel<4, 0> (class 4, non-first sweep), simscore3, planemap3
 mkdir -p gpurun_out
 CFG=${1:-c3}
-TAG=${2:-r01}
+TAG=${2:-r02}
 B="python bench.py --config $CFG --steps 1 --warmup 1 --no-cpu --no-e2e"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_${CFG}_${TAG}.csv \
     $B > gpurun_out/bench_under_ncu_${CFG}_${TAG}.log 2>&1

@@ -361,11 +361,23 @@ class RayNetForwardPass(ForwardPass):
             slot = dict((v, k) for k, v in enumerate(all_views))
             n_slots = world * per
         else:
-            f_host = self._predict_views(scene, views)
+            # a model that works on the device (raynet_b200.models.SimpleCNN) runs on the side stream: its image
+            # upload and convolutions overlap with the tracing and binning of the rays, which need no features
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_stream.wait_stream(main)
+            with torch.cuda.stream(self._copy_stream):
+                f_host = self._predict_views(scene, views)
+                if f_host.is_cuda:
+                    f_host = f_host.contiguous()
+                    f_host.record_stream(main)
+                    ready = torch.cuda.Event()
+                    ready.record()
             n_slots = len(views)
             if f_host.is_cuda:
-                # the model produced the feature volume on the device (raynet_b200.models.SimpleCNN): nothing to upload
-                self._feat_dev = f_host.contiguous()
+                self._feat_dev = f_host          # produced on the device: nothing to upload
+                for k in range(n_slots):
+                    copied[k] = ready
             else:
                 if self._feat_dev is None or self._feat_dev.shape != f_host.shape:
                     self._feat_dev = torch.empty(f_host.shape, dtype=torch.float32, device=dev)
@@ -377,10 +389,7 @@ class RayNetForwardPass(ForwardPass):
                     stage = self._pinned("features", tuple(f_host.shape), torch.float32)
                     stage.copy_(f_host)
                     f_host = stage
-                if self._copy_stream is None:
-                    self._copy_stream = torch.cuda.Stream(device=dev)
-                self._copy_stream.wait_stream(main)      # the previous call's readers of _feat_dev are done
-                with torch.cuda.stream(self._copy_stream):
+                with torch.cuda.stream(self._copy_stream):      # (it already waits for the previous call's readers)
                     for k in first_use:
                         self._feat_dev[k].copy_(f_host[k], non_blocking=True)
                         copied[k] = torch.cuda.Event()

@@ -57,6 +57,12 @@ __device__ __forceinline__ float rn_occ_w2(float acc, float msg) {
 #ifndef RN_BP4_WAIT_ONE
 #define RN_BP4_WAIT_ONE 0
 #endif
+#ifndef RN_BP4_TMA_HINT
+#define RN_BP4_TMA_HINT 1      // L2 evict-first hint on the bulk copies
+#endif
+#ifndef RN_BP4_TMA_FENCE
+#define RN_BP4_TMA_FENCE 1     // proxy fence before a buffer goes back to the async proxy
+#endif
 #ifndef RN_BP4_TMA
 // 0: rows staged by per-lane 16-byte cp.async (LDGSTS); 1: by cp.async.bulk + mbarrier (TMA, UBLKCP).
 // Measured on C3 (B200, same box, ms per non-first sweep; profiles/README.md): LDGSTS 3.78, TMA 4.15 -- a ray's
@@ -65,6 +71,10 @@ __device__ __forceinline__ float rn_occ_w2(float acc, float msg) {
 #define RN_BP4_TMA 0
 #endif
 
+__device__ __forceinline__ void rn_bulk_g2s_nohint(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void rn_cp_async16(uint32_t dst_smem, const void *src, uint64_t pol) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(pol) : "memory");
 }
@@ -125,9 +135,15 @@ __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp
                 const uint32_t bytes = (uint32_t)((L + 3) & ~3) * 4u;
                 const uint32_t bar = rn_smem_u32(&bars[wid][b]);
                 rn_mbar_expect_tx(bar, bytes * (kFirst ? 2u : 3u));
+#if RN_BP4_TMA_HINT
                 rn_bulk_g2s(rn_smem_u32(base + b * ROW), lin_row, bytes, bar, pol_stream);
                 rn_bulk_g2s(rn_smem_u32(base + (2 + b) * ROW), s_row, bytes, bar, pol_stream);
                 if (!kFirst) rn_bulk_g2s(rn_smem_u32(base + (4 + b) * ROW), m_row, bytes, bar, pol_stream);
+#else
+                rn_bulk_g2s_nohint(rn_smem_u32(base + b * ROW), lin_row, bytes, bar);
+                rn_bulk_g2s_nohint(rn_smem_u32(base + (2 + b) * ROW), s_row, bytes, bar);
+                if (!kFirst) rn_bulk_g2s_nohint(rn_smem_u32(base + (4 + b) * ROW), m_row, bytes, bar);
+#endif
             }
         } else {
 #pragma unroll
@@ -156,7 +172,7 @@ __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp
         const int L = L_cur;
         // every lane is done with the buffers of ray t - 1; its generic-proxy stores into them (transposition
         // scratch) are ordered before the async-proxy writes of the next bulk copy
-        if (kTma) rn_fence_async_smem();
+        if (kTma && RN_BP4_TMA_FENCE) rn_fence_async_smem();
         __syncwarp();
         if (t + 1 < nmine) {
             prefetch(r_nxt, L_nxt, b ^ 1);

@@ -17,9 +17,12 @@ from rig import Case, case_c1, case_dense, case_long, case_nine, case_small, cas
 pytestmark = pytest.mark.gpu
 
 TOL_P = 1e-5          # absolute tolerance on probabilities (north star)
-# float32 scatter-adds after up to 5 sweeps: BP amplifies the last-digit rounding of the accumulator ~40x
-# over five sweeps (the reference's own f32 and f64 flavours differ by 2e-5 .. 6e-5)
-FAST_MULTI_SWEEP_TOL = 1e-4
+# Fast mode (float32 scatter-adds) after up to 5 sweeps.  BP amplifies the last-digit rounding of the accumulator
+# from sweep to sweep (SURVEY.md 7 measured 2e-5 between the reference's own f32 and f64 flavours on its probe);
+# on every case below the fast kernels measure <= 3.9e-6 (profiles/r02_parity.json: the dense 20-rays-per-voxel
+# case is the worst), so the fast mode is held to the north star's 1e-5 as well.  Parity mode is the one that
+# guarantees it independently of the data.
+FAST_MULTI_SWEEP_TOL = 1e-5
 PRIOR = float(np.float32(np.log(0.05) - np.log(1 - 0.05)))
 
 

@@ -404,27 +404,53 @@ def run_gpu_arm(args, cfg):
     scaling = scaling_of(args, cfg)
     H, W, G, V, D, M, I = (cfg[k] for k in ("H", "W", "G", "V", "D", "M", "I"))
     scene = make_scene(cfg, world, scaling)
-    segs = segments_of_rank(cfg, scene, rank, world, scaling)       # this rank's (image, first ray, last ray)
-    my_images = sorted(set(i for (i, _, _) in segs))
-    my_views = sorted(set(v for i in my_images for v in scene.view_order(i)))
-    model = FeatureModel(my_views, H, W)
-    n_rays = int(sum(b - a for (_, a, b) in segs))
     dev = torch.device("cuda", local)
-
-    # ---------------- device-resident arm -------------------------------------------------------
-    eng = RayPotentialEngine(M, D, V, F, H, W, PADDING, scene.bbox.ravel(), (G, G, G), gamma=GAMMA, max_rays=n_rays,
-                             collective=args.collective)
-    eng.set_voxel_grid(scene.voxel_grid())
-    feats = model.host.to(dev)
-    slot = dict((v, k) for k, v in enumerate(my_views))
-    per_seg = []
     ids = torch.arange(H * W, dtype=torch.int32, device=dev)
-    for (i, a, b) in segs:
-        order = scene.view_order(i)
-        P, P_inv, centre = camera_arrays([scene.get_image(j) for j in order])
-        per_seg.append((ids[a:b], torch.from_numpy(P).to(dev), torch.from_numpy(P_inv).to(dev),
-                        torch.from_numpy(centre).to(dev),
-                        torch.tensor([slot[v] for v in order], dtype=torch.int32, device=dev)))
+
+    def setup(segs, capacity):
+        """Device-resident inputs of this rank's segments [(image, first ray, last ray)] + the engine."""
+        my_images = sorted(set(i for (i, _, _) in segs))
+        my_views = sorted(set(v for i in my_images for v in scene.view_order(i)))
+        model = FeatureModel(my_views, H, W)
+        eng = RayPotentialEngine(M, D, V, F, H, W, PADDING, scene.bbox.ravel(), (G, G, G), gamma=GAMMA, max_rays=capacity,
+                                 collective=args.collective, fuse_first_sweep=not args.no_fuse)
+        eng.set_voxel_grid(scene.voxel_grid())
+        feats = model.host.to(dev)
+        slot = dict((v, k) for k, v in enumerate(my_views))
+        per_seg = []
+        for (i, a, b) in segs:
+            order = scene.view_order(i)
+            P, P_inv, centre = camera_arrays([scene.get_image(j) for j in order])
+            per_seg.append((ids[a:b], torch.from_numpy(P).to(dev), torch.from_numpy(P_inv).to(dev),
+                            torch.from_numpy(centre).to(dev),
+                            torch.tensor([slot[v] for v in order], dtype=torch.int32, device=dev)))
+        return eng, feats, per_seg, my_views
+
+    segs = segments_of_rank(cfg, scene, rank, world, scaling)       # this rank's (image, first ray, last ray)
+    n_rays = int(sum(b - a for (_, a, b) in segs))
+    eng, feats, per_seg, my_views = setup(segs, n_rays)
+    balanced = False
+    if world > 1 and scaling == "strong" and (H * W) % (8 * H) == 0 and not args.no_balance:
+        # blocks of equal WORK instead of equal ray counts (rays near the image border cross few voxels): one
+        # tracing pass gives the traversed voxels per group of 8 image columns, summed over the ranks; the plan is
+        # what RayNetForwardPass caches per job after its first call (raynet_b200/sharding.py)
+        from raynet_b200 import sharding
+        for (sid, P, P_inv, centre, vids) in per_seg:
+            eng.trace_image(sid, P_inv, centre)
+        unit = 8 * H
+        lens = [H * W] * scene.n_images
+        work = torch.zeros((sum(lens) // unit,), dtype=torch.float64, device=dev)
+        lo_u = (segs[0][0] * H * W + segs[0][1]) // unit
+        work[lo_u:lo_u + n_rays // unit] = eng.unit_work(unit)
+        dist.all_reduce(work)
+        bounds = sharding.balanced_boundaries(work.cpu().numpy(), world)
+        all_segs = [sharding.segments_from_unit_boundaries(lens, unit, bounds[r], bounds[r + 1]) for r in range(world)]
+        segs = all_segs[rank]
+        n_rays = int(sum(b - a for (_, a, b) in segs))
+        del eng, feats, per_seg
+        torch.cuda.empty_cache()
+        eng, feats, per_seg, my_views = setup(segs, max(sum(b - a for (_, a, b) in sg) for sg in all_segs))
+        balanced = True
     stage_events = []
 
     def device_step(record=False):
@@ -472,11 +498,16 @@ def run_gpu_arm(args, cfg):
         device_step()
     proc, path = start_clock_sampler(local) if rank == 0 else (None, None)
     eng.sweep_events = []
+    eng.exchange_events = [] if world > 1 else None
     launches0 = eng.launches
     ms_step = timed(lambda: device_step(record=True), args.steps)
     gpu_launches = (eng.launches - launches0) // args.steps
     sweep_ms = np.array([a.elapsed_time(b) for (a, b) in eng.sweep_events]).reshape(args.steps, I)
     eng.sweep_events = None
+    exchange_ms = None
+    if eng.exchange_events:
+        exchange_ms = float(np.mean([a.elapsed_time(b) for (a, b) in eng.exchange_events]))
+    eng.exchange_events = None
     clocks = stop_clock_sampler(proc, path) if rank == 0 else None
     stages = np.array([[e[k].elapsed_time(e[k + 1]) for k in range(3)] for e in stage_events])
     counts = eng.count[:eng.n_rays]
@@ -491,7 +522,7 @@ def run_gpu_arm(args, cfg):
 
     collective = eng.collective
     e2e = None
-    del eng, feats, model
+    del eng, feats
     torch.cuda.empty_cache()
     if not args.no_e2e:
         e2e = run_e2e(args, cfg, rank, world, dev, barrier, total_rays, scaling)
@@ -519,7 +550,9 @@ def run_gpu_arm(args, cfg):
         # per-stage byte model of SURVEY.md 8d (per GPU): front end = 24 B/ray + 4 B per voxel (S_vox written) + the
         # feature maps once; depth = 12 B per voxel + 4 B per ray; grid work = 3 x 4 B x G^3 per sweep
         feat_bytes = len(my_views) * (H + PADDING + 1) * (W + PADDING + 1) * F * 4.0
-        fe_bytes = 24.0 * n_rays + 4.0 * sum_L + feat_bytes
+        # (fused first sweep: the 4 B/voxel S_vox write of the front end happens inside the first sweep, which in turn
+        # no longer reads s_hat -- its 12 B/voxel stay 12 -- and the front end writes 4 D bytes of plane scores per ray)
+        fe_bytes = 24.0 * n_rays + feat_bytes + ((4.0 * D * n_rays) if not args.no_fuse else 4.0 * sum_L)
         de_bytes = 12.0 * sum_L + 4.0 * n_rays
         grid_bytes = I * 3 * G ** 3 * 4.0
         fe_ms, bp_ms, de_ms = (float(stages[:, k].mean()) for k in range(3))
@@ -536,8 +569,11 @@ def run_gpu_arm(args, cfg):
                 "workload": cfg["label"], "rays_total": total_rays, "rays_on_rank0": n_rays,
                 "segments_on_rank0": [[int(i), int(a), int(b)] for (i, a, b) in segs], "bp_sweeps": I, "max_voxels": M,
                 "mean_voxels_per_ray": mean_L, "longest_ray": max_L,
-                "parallelism": "rays sharded in %d contiguous blocks of the (image, pixel) enumeration" % world
+                "parallelism": ("rays sharded in %d contiguous blocks of the (image, pixel) enumeration, %s" %
+                                (world, "cut for equal traversed voxels" if balanced else "equal ray counts"))
                                if scaling == "strong" else "whole reference images per rank, dp%d" % world,
+                "first_sweep": "plane->voxel mapping fused into the first sweep (rn_engine_first_sweep_mapped)"
+                               if not args.no_fuse else "separate mapping kernel",
                 "collective": ("sum of the per-rank partial f32[%d^3] accumulators after every sweep: %s" % (G, {
                     "peer": "this library's fused barrier + reduce + broadcast kernel over NVLink peer memory "
                             "(rn_peer_allreduce_f32)"}.get(collective, "torch.distributed all_reduce, " + collective)))
@@ -554,7 +590,8 @@ def run_gpu_arm(args, cfg):
                           "ray-length class, timed with CUDA events around the launch set",
                 "algorithmic_bytes_per_launch": b_next, "launch_ms": next_ms,
                 "launches_timed": int(sweep_ms[:, 1:].size), "peak_source": peak_src,
-                "first_sweep": {"kernel": "bp4_kernel<NCH, true>", "algorithmic_bytes_per_launch": b_first,
+                "first_sweep": {"kernel": "bp4_first_mapped_kernel<NCH> (plane->voxel mapping + first sweep)" if not args.no_fuse
+                                else "bp4_kernel<NCH, true>", "algorithmic_bytes_per_launch": b_first,
                                 "launch_ms": first_ms, "achieved": a_first, "frac": a_first / peak},
                 "all_sweeps": {"algorithmic_bytes": blend_bytes, "ms": blend_ms, "frac": frac(blend_bytes, blend_ms)},
                 "stages": {
@@ -567,7 +604,7 @@ def run_gpu_arm(args, cfg):
                 "step_model": {"bytes_per_step_per_gpu": step_bytes, "frac_of_peak": frac(step_bytes, ms_step)},
             },
             "stages_ms": {"frontend": fe_ms, "bp": bp_ms, "depth": de_ms,
-                          "bp_first_sweep": first_ms, "bp_next_sweep": next_ms},
+                          "bp_first_sweep": first_ms, "bp_next_sweep": next_ms, "exchange_incl_wait_for_slowest_rank": exchange_ms},
             "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
         }
         if cnn is not None:
@@ -600,6 +637,8 @@ def main():
                     help="strong: the fixed job sharded by rays over the GPUs (default); weak: fixed work per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs only)")
+    ap.add_argument("--no-fuse", action="store_true", help="separate plane->voxel mapping kernel instead of the fused first sweep")
+    ap.add_argument("--no-balance", action="store_true", help="strong scaling: blocks of equal ray counts instead of equal work")
     ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
                     help="exchange step of the multi-GPU path (engine.py); auto = peer kernel when the GPUs map each other")
     args = ap.parse_args()

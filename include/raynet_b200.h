@@ -378,11 +378,35 @@ int rn_depth_loss(const RnParams *p, int32_t kind, const float *y_true, const fl
  * mappings, e.g. torch.distributed._symmetric_memory); flags: uint32 [n_ctas][world] per rank, zeroed once;
  * epoch: 2 x the number of earlier calls on these flags (the same on all ranks); n_ctas <= SM count (all CTAs
  * of all ranks must be resident: a CTA waits for its twin on every peer); n: float32 elements, multiple of 4.
- * Replaces ncclAllReduce + the prior epilogue; the reference has no multi-GPU code.
+ * zero_next_partial (may be NULL): a LOCAL buffer of n floats cleared by the same kernel -- the partial of the next
+ * sweep when the caller double-buffers its partials (nobody reads it between two exchanges), which removes the
+ * fill launch between sweeps.  Replaces ncclAllReduce + the prior epilogue + the fill; the reference has no
+ * multi-GPU code.
  * ------------------------------------------------------------------------------------- */
 int rn_peer_allreduce_f32(const uint64_t *peer_partials, const uint64_t *peer_results, const uint64_t *peer_flags,
-                          int32_t rank, int32_t world, int32_t n_ctas, uint32_t epoch, float prior, int64_t n,
-                          void *stream);
+                          float *zero_next_partial, int32_t rank, int32_t world, int32_t n_ctas, uint32_t epoch,
+                          float prior, int64_t n, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Plane->voxel mapping fused into the first sweep.  rn_engine_similarity = rn_engine_plane_scores (a2: plane-sweep
+ * similarity + softmax -> S_planes float32 [n][depth_planes], feat_dim == 32 only) followed by rn_engine_map_planes
+ * (a4 + clip_and_renorm -> s_hat, lin).  A caller that is about to run the FIRST sweep straight after a reset (uniform
+ * accumulator, no messages) can skip rn_engine_map_planes: rn_engine_first_sweep_mapped builds the rows of every ray
+ * inside the sweep kernel (identical arithmetic), uses them in place, writes them once for the later sweeps, and
+ * also maps the rays BP skips.  acc_in: any address holding the accumulator's uniform value (the prior).
+ * Replaces planes_voxels_mapping.cu:94-118 + mrf_bp.cu:180-204 for that sweep.
+ * ------------------------------------------------------------------------------------- */
+int rn_engine_plane_scores(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
+                           const float *P, const float *starts, const float *ends, float *S_planes, int64_t n_rays,
+                           void *stream);
+int rn_engine_map_planes(const RnParams *p, const float *axis_centres, const float *starts, const float *ends,
+                         const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count, const float *S_planes,
+                         float *s_hat, int32_t *lin, int64_t n_rays, void *stream);
+int rn_engine_first_sweep_mapped(const RnParams *p, const float *axis_centres, const float *starts, const float *ends,
+                                 const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count,
+                                 const float *S_planes, int32_t *lin, float *s_hat, float *msgs, const float *acc_in,
+                                 float *acc_out, const int32_t *order, const int64_t *class_offsets, int64_t n_rays,
+                                 void *stream);
 
 #ifdef __cplusplus
 }

@@ -97,8 +97,12 @@ SIGNATURES = {
     "rn_planes_to_voxels_backward": [_PP] + [_PTR] * 7 + [_I32] + [_PTR] * 3 + [_I64, _PTR],
     "rn_clip_renorm_backward": [_PP] + [_PTR] * 4 + [_I64, _PTR],
     "rn_depth_loss": [_PP, _I32] + [_PTR] * 7 + [ctypes.c_float, _I64, _PTR],
+    # mapping fused into the first sweep
+    "rn_engine_plane_scores": [_PP, _PTR, _PTR, _I32] + [_PTR] * 4 + [_I64, _PTR],
+    "rn_engine_map_planes": [_PP] + [_PTR] * 9 + [_I64, _PTR],
+    "rn_engine_first_sweep_mapped": [_PP] + [_PTR] * 14 + [_I64, _PTR],
     # exchange step over NVLink peer memory
-    "rn_peer_allreduce_f32": [_PTR, _PTR, _PTR, _I32, _I32, _I32, ctypes.c_uint32, ctypes.c_float, _I64, _PTR],
+    "rn_peer_allreduce_f32": [_PTR, _PTR, _PTR, _PTR, _I32, _I32, _I32, ctypes.c_uint32, ctypes.c_float, _I64, _PTR],
 }
 OTHER_SYMBOLS = ["rn_last_error", "rn_abi_version", "rn_device_info", "rn_code_stride", "rn_row_stride", "rn_num_classes",
                  "rn_brick_elems", "rn_backward_scratch_bytes"]

@@ -11,6 +11,7 @@
 #include "rn_backward.cuh"
 #include "rn_peer.cuh"
 #include "rn_simmap3.cuh"
+#include "rn_first.cuh"
 #include "rn_cnn.cuh"
 #include "rn_fusion.cuh"
 
@@ -183,30 +184,57 @@ int launch_simscore3(const RnDev &d, const SimMapArgs &a, size_t smem, cudaStrea
     return check_launch("simscore3_kernel");
 }
 
-int launch_simmap3(const RnDev &d, SimMapArgs a, float *plane_scratch, cudaStream_t st) {
+int launch_plane_scores(const RnDev &d, SimMapArgs a, cudaStream_t st) {
     if (a.n_rays <= 0) return RN_OK;
-    a.S_planes = plane_scratch;
-    a.val_stride = (int)row_stride_of(d.M);
     a.tile_len = tile_len_for(d, a.n_rays);
     a.tile_mode = 2;
     const size_t smem_a = simscore3_smem(d);
-    const size_t smem_b = sizeof(float) * (rn_planemap3_cta_words(d.gx + d.gy + d.gz) + 4 * rn_planemap3_warp_words(d.D, a.val_stride));
-    int rc;
     switch (d.V) {   // common view counts get fully unrolled loops
-        case 3: rc = launch_simscore3<3>(d, a, smem_a, st); break;
-        case 5: rc = launch_simscore3<5>(d, a, smem_a, st); break;
-        case 7: rc = launch_simscore3<7>(d, a, smem_a, st); break;
-        case 9: rc = launch_simscore3<9>(d, a, smem_a, st); break;
-        case 11: rc = launch_simscore3<11>(d, a, smem_a, st); break;
-        case 15: rc = launch_simscore3<15>(d, a, smem_a, st); break;
-        default: rc = launch_simscore3<0>(d, a, smem_a, st); break;
+        case 3: return launch_simscore3<3>(d, a, smem_a, st);
+        case 5: return launch_simscore3<5>(d, a, smem_a, st);
+        case 7: return launch_simscore3<7>(d, a, smem_a, st);
+        case 9: return launch_simscore3<9>(d, a, smem_a, st);
+        case 11: return launch_simscore3<11>(d, a, smem_a, st);
+        case 15: return launch_simscore3<15>(d, a, smem_a, st);
     }
-    if (rc) return rc;
+    return launch_simscore3<0>(d, a, smem_a, st);
+}
+
+int launch_planemap3(const RnDev &d, SimMapArgs a, cudaStream_t st) {
+    if (a.n_rays <= 0) return RN_OK;
+    a.val_stride = (int)row_stride_of(d.M);
+    const size_t smem_b = sizeof(float) * (rn_planemap3_cta_words(d.gx + d.gy + d.gz) + 4 * rn_planemap3_warp_words(d.D, a.val_stride));
     static SmemOptIn opt_b;
-    if ((rc = opt_b.ensure(planemap3_kernel, smem_b, "planemap3_kernel"))) return rc;
+    if (int rc = opt_b.ensure(planemap3_kernel, smem_b, "planemap3_kernel")) return rc;
     const int64_t per_cta = 4 * RN_SM3_RAYS_PER_WARP;
     planemap3_kernel<<<(unsigned)((a.n_rays + per_cta - 1) / per_cta), 128, smem_b, st>>>(d, a);
     return check_launch("planemap3_kernel");
+}
+
+int launch_simmap3(const RnDev &d, SimMapArgs a, float *plane_scratch, cudaStream_t st) {
+    a.S_planes = plane_scratch;
+    int rc = launch_plane_scores(d, a, st);
+    if (rc) return rc;
+    return launch_planemap3(d, a, st);
+}
+
+// the F = 32 kernels address the feature volume with 32-bit BYTE offsets (below 4 GiB only) and keep
+// depth_planes x n_views offsets per warp in shared memory
+inline bool simmap3_applies(const RnDev &d, const int32_t *view_ids, int32_t n_feature_slots) {
+    const int64_t feat_elems = (int64_t)(view_ids ? n_feature_slots : d.V) * d.fh * d.fw * d.F;
+    return d.F == 32 && feat_elems < (1ll << 30) && simscore3_smem(d) <= 200 * 1024;
+}
+
+// Mapping fused into the first sweep (rn_first.cuh); every ray of the launch has exactly NCH chunks.
+template <int NCH>
+int launch_first_mapped(const RnDev &d, FirstArgs a, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (rn_first_cta_words(d.gx + d.gy + d.gz) + 4 * rn_first_warp_words(d.D, NCH));
+    static SmemOptIn opt;
+    if (int rc = opt.ensure(bp4_first_mapped_kernel<NCH>, smem, "bp4_first_mapped_kernel")) return rc;
+    a.rays_per_warp = RN_BP4_RAYS_PER_WARP;
+    const int per_cta = 4 * a.rays_per_warp;
+    bp4_first_mapped_kernel<NCH><<<(unsigned)((a.n + per_cta - 1) / per_cta), 128, smem, st>>>(d, a);
+    return check_launch("bp4_first_mapped_kernel");
 }
 
 // one conv + folded BN (+ ReLU) layer of the MV-CNN (rn_cnn.cuh)
@@ -672,10 +700,7 @@ int rn_engine_similarity(const RnParams *p, const float *features, const int32_t
     a.features = features; a.view_ids = view_ids; a.P = P;
     a.axes = axis_centres; a.hdr = ray_hdr; a.codes = codes; a.count = count; a.s_hat = s_hat; a.lin = lin;
     a.n_rays = n_rays;
-    // the F = 32 kernels address the feature volume with 32-bit BYTE offsets (below 4 GiB only) and keep
-    // depth_planes x n_views offsets per warp in shared memory; anything else takes the generic kernel
-    const int64_t feat_elems = (int64_t)(view_ids ? n_feature_slots : d.V) * d.fh * d.fw * d.F;
-    if (d.F == 32 && feat_elems < (1ll << 30) && simscore3_smem(d) <= 200 * 1024) {
+    if (simmap3_applies(d, view_ids, n_feature_slots)) {   // anything else takes the generic kernel
         if (!plane_scratch) return fail(RN_ERR_SHAPE, "rn_engine_similarity needs plane_scratch (n_rays x depth_planes floats)");
         return launch_simmap3(d, a, plane_scratch, S(stream));
     }
@@ -989,8 +1014,8 @@ int rn_depth_loss(const RnParams *p, int32_t kind, const float *y_true, const fl
 
 // ---- the exchange step over NVLink peer memory (rn_peer.cuh) ----------------------------------------------------
 int rn_peer_allreduce_f32(const uint64_t *peer_partials, const uint64_t *peer_results, const uint64_t *peer_flags,
-                          int32_t rank, int32_t world, int32_t n_ctas, uint32_t epoch, float prior, int64_t n,
-                          void *stream) {
+                          float *zero_next_partial, int32_t rank, int32_t world, int32_t n_ctas, uint32_t epoch,
+                          float prior, int64_t n, void *stream) {
     if (world < 1 || world > RN_PEER_MAX_WORLD || rank < 0 || rank >= world)
         return fail(RN_ERR_UNSUPPORTED, "rn_peer_allreduce_f32: world size must be in [1, %d]", RN_PEER_MAX_WORLD);
     if (!peer_partials || !peer_results || !peer_flags) return fail(RN_ERR_SHAPE, "rn_peer_allreduce_f32: NULL pointer table");
@@ -1007,9 +1032,87 @@ int rn_peer_allreduce_f32(const uint64_t *peer_partials, const uint64_t *peer_re
         a.flags[p] = reinterpret_cast<uint32_t *>(peer_flags[p]);
         if (!a.partial[p] || !a.result[p] || !a.flags[p]) return fail(RN_ERR_SHAPE, "rn_peer_allreduce_f32: NULL peer pointer");
     }
+    a.zero = zero_next_partial;
     a.rank = rank; a.world = world; a.epoch = epoch; a.prior = prior; a.n = n;
-    peer_allreduce_kernel<<<(unsigned)n_ctas, 512, 0, S(stream)>>>(a);
+    switch (world) {
+        case 2: peer_allreduce_kernel<2><<<(unsigned)n_ctas, 512, 0, S(stream)>>>(a); break;
+        case 4: peer_allreduce_kernel<4><<<(unsigned)n_ctas, 512, 0, S(stream)>>>(a); break;
+        case 8: peer_allreduce_kernel<8><<<(unsigned)n_ctas, 512, 0, S(stream)>>>(a); break;
+        default: peer_allreduce_kernel<0><<<(unsigned)n_ctas, 512, 0, S(stream)>>>(a); break;
+    }
     return check_launch("peer_allreduce_kernel");
+}
+
+// ---- mapping fused into the first sweep (rn_first.cuh) ------------------------------------------------------------
+int rn_engine_plane_scores(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
+                           const float *P, const float *starts, const float *ends, float *S_planes, int64_t n_rays,
+                           void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, true, true);
+    if (rc) return rc;
+    if (n_rays <= 0) return RN_OK;
+    if (!starts || !ends || !S_planes) return fail(RN_ERR_SHAPE, "rn_engine_plane_scores: NULL buffer");
+    if (view_ids && n_feature_slots < 1) return fail(RN_ERR_SHAPE, "n_feature_slots must be positive when view_ids is given");
+    if (!simmap3_applies(d, view_ids, n_feature_slots))
+        return fail(RN_ERR_UNSUPPORTED, "rn_engine_plane_scores needs feat_dim == 32 and a feature volume below 4 GiB (use rn_engine_similarity)");
+    SimMapArgs a = {};
+    a.starts_in = starts; a.ends_in = ends; a.features = features; a.view_ids = view_ids; a.P = P;
+    a.S_planes = S_planes; a.n_rays = n_rays;
+    return launch_plane_scores(d, a, S(stream));
+}
+
+int rn_engine_map_planes(const RnParams *p, const float *axis_centres, const float *starts, const float *ends,
+                         const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count, const float *S_planes,
+                         float *s_hat, int32_t *lin, int64_t n_rays, void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, true);
+    if (rc) return rc;
+    if (d.D < 2 || d.D > 128) return fail(RN_ERR_UNSUPPORTED, "depth_planes must be in [2, 128]");
+    if (n_rays <= 0) return RN_OK;
+    SimMapArgs a = {};
+    a.starts_in = starts; a.ends_in = ends; a.axes = axis_centres; a.hdr = ray_hdr; a.codes = codes; a.count = count;
+    a.S_planes = const_cast<float *>(S_planes); a.s_hat = s_hat; a.lin = lin; a.n_rays = n_rays;
+    return launch_planemap3(d, a, S(stream));
+}
+
+int rn_engine_first_sweep_mapped(const RnParams *p, const float *axis_centres, const float *starts, const float *ends,
+                                 const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count,
+                                 const float *S_planes, int32_t *lin, float *s_hat, float *msgs, const float *acc_in,
+                                 float *acc_out, const int32_t *order, const int64_t *class_offsets, int64_t n_rays,
+                                 void *stream) {
+    RnDev d;
+    int rc = make_dev(p, d, true, false, true);
+    if (rc) return rc;
+    if (d.D < 2 || d.D > 128) return fail(RN_ERR_UNSUPPORTED, "depth_planes must be in [2, 128]");
+    if (!order || !class_offsets) return fail(RN_ERR_SHAPE, "rn_engine_first_sweep_mapped needs the binning of rn_engine_bin_rays");
+    FirstArgs a = {};
+    a.axes = axis_centres; a.starts = starts; a.ends = ends; a.hdr = ray_hdr; a.codes = codes; a.count = count;
+    a.S_planes = S_planes; a.lin = lin; a.s_hat = s_hat; a.msgs = msgs; a.acc_in = acc_in; a.acc_out = acc_out;
+    a.order = order;
+    for (int c = RN_NCLASS - 1; c >= 0; c--) {
+        a.first = class_offsets[c];
+        a.n = class_offsets[c + 1] - class_offsets[c];
+        if (a.first < 0 || a.n < 0 || a.first + a.n > n_rays) return fail(RN_ERR_SHAPE, "class_offsets out of range");
+        if (a.n == 0) continue;
+        a.map_only = (c == 0) ? 1 : 0;   // the rays BP skips (count <= 1) still get their rows: the depth pass reads lin[0]
+        switch (c == 0 ? 1 : c) {
+            case 1: rc = launch_first_mapped<1>(d, a, S(stream)); break;
+            case 2: rc = launch_first_mapped<2>(d, a, S(stream)); break;
+            case 3: rc = launch_first_mapped<3>(d, a, S(stream)); break;
+            case 4: rc = launch_first_mapped<4>(d, a, S(stream)); break;
+            case 5: rc = launch_first_mapped<5>(d, a, S(stream)); break;
+            case 6: rc = launch_first_mapped<6>(d, a, S(stream)); break;
+            case 7: rc = launch_first_mapped<7>(d, a, S(stream)); break;
+            case 8: rc = launch_first_mapped<8>(d, a, S(stream)); break;
+            case 9: rc = launch_first_mapped<9>(d, a, S(stream)); break;
+            case 10: rc = launch_first_mapped<10>(d, a, S(stream)); break;
+            case 11: rc = launch_first_mapped<11>(d, a, S(stream)); break;
+            case 12: rc = launch_first_mapped<12>(d, a, S(stream)); break;
+            default: rc = fail(RN_ERR_UNSUPPORTED, "length class %d", c);
+        }
+        if (rc) return rc;
+    }
+    return RN_OK;
 }
 
 }  // extern "C"

@@ -89,6 +89,136 @@ __host__ __device__ constexpr int rn_bp4_warps(int nch) { return nch <= 6 ? 4 : 
 // four values per lane have been read.
 __host__ __device__ constexpr int rn_bp4_warp_words(int nch, bool first) { return nch * RN_CHUNK * (first ? 4 : 6); }
 
+// One ray of a sweep, shared by bp4_kernel and bp4_first_mapped_kernel.  sLin / sS (/ sM unless kFirst): the ray's
+// rows in shared memory, NCH chunks of 128; sS doubles as the transposition scratch (chunk c is dead once its four
+// values per lane have been read).  uniform (first sweep straight after a reset): the accumulator is the prior
+// everywhere -- one load, no gathers.
+template <int NCH, bool kFirst>
+__device__ __forceinline__ void rn_bp4_ray(const float *acc_in, float *acc_out, const bool uniform, const int *sLin, float *sS,
+                                           const float *sM, float *m_row, const int L, const int lane,
+                                           const uint64_t pol_stream, const uint64_t pol_keep) {
+    // ---- accumulator gathers, lane-consecutive (neighbouring lanes share sectors) -------------
+    // (first sweep straight after a reset: the accumulator is the prior everywhere -- one load)
+    float ga[NCH][4];
+    if (uniform) {
+        const float acc0 = __ldg(acc_in);
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) ga[c][j] = acc0;
+    } else {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = c * RN_CHUNK + 32 * j + lane;
+                ga[c][j] = 0.f;
+                if (c < NCH - 1 || i < L) ga[c][j] = rn_ld_acc_pol(acc_in + sLin[i], pol_keep);
+            }
+        }
+    }
+
+    // ---- forward: occupancy-to-ray values, prefix scans ----------------------------------------
+    float w[NCH][4], cps[NCH][4], pre0[NCH], tot[NCH];
+    float carry_cp = 1.f, carry_pre = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int i0 = c * RN_CHUNK + 4 * lane;
+        const float4 s4 = *reinterpret_cast<const float4 *>(sS + i0);
+        float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);   // first sweep: messages are 0 (mrf_np.py:275)
+        if (!kFirst) m4 = *reinterpret_cast<const float4 *>(sM + i0);
+        float accv[4];
+        if (uniform) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) accv[j] = ga[c][j];
+        } else {   // lane-consecutive -> 4 consecutive voxels per lane, through the s_hat chunk just read
+            float *sX = sS + c * RN_CHUNK;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; j++) sX[32 * j + lane] = ga[c][j];
+            __syncwarp();
+            const float4 acc4 = *reinterpret_cast<const float4 *>(sX + 4 * lane);
+            accv[0] = acc4.x; accv[1] = acc4.y; accv[2] = acc4.z; accv[3] = acc4.w;
+        }
+        float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+        float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+        float o[4], q[4];
+        if (c == NCH - 1) {
+            // slots beyond the ray: s = 0 (nothing reaches the sums), message 0 (accumulator is 0 already)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool ok = i0 + j < L;
+                sv[j] = ok ? sv[j] : 0.f;
+                mv[j] = ok ? mv[j] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            w[c][j] = rn_occ_w2(accv[j], mv[j]);
+            rn_occ_from_w(w[c][j], o[j], q[j]);
+        }
+        // exclusive products cp_i = prod_{k<i} (1 - o_k)
+        const float lp0 = q[0], lp1 = lp0 * q[1], lp2 = lp1 * q[2], lp3 = lp2 * q[3];
+        const float inc = rn_warp_incl_scan_mul(lp3, lane);
+        float exc = __shfl_up_sync(RN_FULL_MASK, inc, 1);
+        if (lane == 0) exc = 1.f;
+        const float basecp = carry_cp * exc;
+        carry_cp = carry_cp * __shfl_sync(RN_FULL_MASK, inc, 31);
+        cps[c][0] = basecp * sv[0];
+        cps[c][1] = (basecp * lp0) * sv[1];
+        cps[c][2] = (basecp * lp1) * sv[2];
+        cps[c][3] = (basecp * lp2) * sv[3];
+        // prefix sums of a_i = o_i cp_i s_i (true exclusive scan: no cancellation)
+        const float la = fmaf(o[3], cps[c][3], fmaf(o[2], cps[c][2], fmaf(o[1], cps[c][1], o[0] * cps[c][0])));
+        const float sinc = rn_warp_incl_scan_add(la, lane);
+        float sexc = __shfl_up_sync(RN_FULL_MASK, sinc, 1);
+        if (lane == 0) sexc = 0.f;
+        tot[c] = __shfl_sync(RN_FULL_MASK, sinc, 31);
+        pre0[c] = carry_pre + sexc;
+        carry_pre += tot[c];
+    }
+
+    // ---- backward: suffix sums, messages, scatter-add ----------------------------------------------
+    float carry_suf = 0.f;
+#pragma unroll
+    for (int c = NCH - 1; c >= 0; c--) {
+        float o[4], q[4], av[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            rn_occ_from_w(w[c][j], o[j], q[j]);
+            av[j] = o[j] * cps[c][j];
+        }
+        const float ra3 = av[3], ra2 = av[2] + ra3, ra1 = av[1] + ra2, ra0 = av[0] + ra1;
+        // sum over the lanes ABOVE this one: shift, then inclusive reverse scan (exact exclusive)
+        float above = __shfl_down_sync(RN_FULL_MASK, ra0, 1);
+        if (lane == 31) above = 0.f;
+        const float sbase = carry_suf + rn_warp_incl_rscan_add(above, lane);
+        const float suf[4] = {sbase + ra1, sbase + ra2, sbase + ra3, sbase};
+        float pre = pre0[c];
+        float msg[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            // p / (1 - p) = pos / neg, pos = pre + cp s, neg = pre + suf / q  ->  pos q / (pre q + suf)
+            const float pos = pre + cps[c][j];
+            const float den = fmaf(pre, q[j], suf[j]);
+            msg[j] = 0.6931471805599453f * rn_lg2((pos * q[j]) * rn_rcp(den));
+            pre += av[j];
+        }
+        carry_suf += tot[c];
+        const int i0 = c * RN_CHUNK + 4 * lane;
+        const float4 msg4 = make_float4(msg[0], msg[1], msg[2], msg[3]);
+        if (c < NCH - 1 || i0 < L) rn_st_stream4_pol(m_row + i0, msg4, pol_stream);   // rows hold whole quads
+        float *sX = sS + c * RN_CHUNK;   // every chunk has its own scratch: no wait for the previous chunk's readers
+        *reinterpret_cast<float4 *>(sX + 4 * lane) = msg4;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = c * RN_CHUNK + 32 * j + lane;
+            if (c < NCH - 1 || i < L) rn_red_add_pol(acc_out + sLin[i], sX[32 * j + lane], pol_keep);
+        }
+    }
+}
+
 template <int NCH, bool kFirst>
 __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp2Args a) {
     extern __shared__ __align__(128) unsigned char rn_bp4_smem[];
@@ -197,127 +327,7 @@ __global__ void __launch_bounds__(32 * rn_bp4_warps(NCH)) bp4_kernel(RnDev p, Bp
         const float *sM = base + (4 + b) * ROW;   // !kFirst only
         float *m_row = a.msgs + r * (int64_t)p.row_stride;
 
-        // ---- accumulator gathers, lane-consecutive (neighbouring lanes share sectors) -------------
-        // (first sweep straight after a reset: the accumulator is the prior everywhere -- one load)
-        const bool uniform = kFirst && a.uniform_acc;
-        float ga[NCH][4];
-        if (uniform) {
-            const float acc0 = __ldg(a.acc_in);
-#pragma unroll
-            for (int c = 0; c < NCH; c++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) ga[c][j] = acc0;
-        } else {
-#pragma unroll
-            for (int c = 0; c < NCH; c++) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int i = c * RN_CHUNK + 32 * j + lane;
-                    ga[c][j] = 0.f;
-                    if (c < NCH - 1 || i < L) ga[c][j] = rn_ld_acc_pol(a.acc_in + sLin[i], pol_keep);
-                }
-            }
-        }
-
-        // ---- forward: occupancy-to-ray values, prefix scans ----------------------------------------
-        float w[NCH][4], cps[NCH][4], pre0[NCH], tot[NCH];
-        float carry_cp = 1.f, carry_pre = 0.f;
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const int i0 = c * RN_CHUNK + 4 * lane;
-            const float4 s4 = *reinterpret_cast<const float4 *>(sS + i0);
-            float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);   // first sweep: messages are 0 (mrf_np.py:275)
-            if (!kFirst) m4 = *reinterpret_cast<const float4 *>(sM + i0);
-            float accv[4];
-            if (uniform) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) accv[j] = ga[c][j];
-            } else {   // lane-consecutive -> 4 consecutive voxels per lane, through the s_hat chunk just read
-                float *sX = sS + c * RN_CHUNK;
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 4; j++) sX[32 * j + lane] = ga[c][j];
-                __syncwarp();
-                const float4 acc4 = *reinterpret_cast<const float4 *>(sX + 4 * lane);
-                accv[0] = acc4.x; accv[1] = acc4.y; accv[2] = acc4.z; accv[3] = acc4.w;
-            }
-            float mv[4] = {m4.x, m4.y, m4.z, m4.w};
-            float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-            float o[4], q[4];
-            if (c == NCH - 1) {
-                // slots beyond the ray: s = 0 (nothing reaches the sums), message 0 (accumulator is 0 already)
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const bool ok = i0 + j < L;
-                    sv[j] = ok ? sv[j] : 0.f;
-                    mv[j] = ok ? mv[j] : 0.f;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                w[c][j] = rn_occ_w2(accv[j], mv[j]);
-                rn_occ_from_w(w[c][j], o[j], q[j]);
-            }
-            // exclusive products cp_i = prod_{k<i} (1 - o_k)
-            const float lp0 = q[0], lp1 = lp0 * q[1], lp2 = lp1 * q[2], lp3 = lp2 * q[3];
-            const float inc = rn_warp_incl_scan_mul(lp3, lane);
-            float exc = __shfl_up_sync(RN_FULL_MASK, inc, 1);
-            if (lane == 0) exc = 1.f;
-            const float basecp = carry_cp * exc;
-            carry_cp = carry_cp * __shfl_sync(RN_FULL_MASK, inc, 31);
-            cps[c][0] = basecp * sv[0];
-            cps[c][1] = (basecp * lp0) * sv[1];
-            cps[c][2] = (basecp * lp1) * sv[2];
-            cps[c][3] = (basecp * lp2) * sv[3];
-            // prefix sums of a_i = o_i cp_i s_i (true exclusive scan: no cancellation)
-            const float la = fmaf(o[3], cps[c][3], fmaf(o[2], cps[c][2], fmaf(o[1], cps[c][1], o[0] * cps[c][0])));
-            const float sinc = rn_warp_incl_scan_add(la, lane);
-            float sexc = __shfl_up_sync(RN_FULL_MASK, sinc, 1);
-            if (lane == 0) sexc = 0.f;
-            tot[c] = __shfl_sync(RN_FULL_MASK, sinc, 31);
-            pre0[c] = carry_pre + sexc;
-            carry_pre += tot[c];
-        }
-
-        // ---- backward: suffix sums, messages, scatter-add ----------------------------------------------
-        float carry_suf = 0.f;
-#pragma unroll
-        for (int c = NCH - 1; c >= 0; c--) {
-            float o[4], q[4], av[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                rn_occ_from_w(w[c][j], o[j], q[j]);
-                av[j] = o[j] * cps[c][j];
-            }
-            const float ra3 = av[3], ra2 = av[2] + ra3, ra1 = av[1] + ra2, ra0 = av[0] + ra1;
-            // sum over the lanes ABOVE this one: shift, then inclusive reverse scan (exact exclusive)
-            float above = __shfl_down_sync(RN_FULL_MASK, ra0, 1);
-            if (lane == 31) above = 0.f;
-            const float sbase = carry_suf + rn_warp_incl_rscan_add(above, lane);
-            const float suf[4] = {sbase + ra1, sbase + ra2, sbase + ra3, sbase};
-            float pre = pre0[c];
-            float msg[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                // p / (1 - p) = pos / neg, pos = pre + cp s, neg = pre + suf / q  ->  pos q / (pre q + suf)
-                const float pos = pre + cps[c][j];
-                const float den = fmaf(pre, q[j], suf[j]);
-                msg[j] = 0.6931471805599453f * rn_lg2((pos * q[j]) * rn_rcp(den));
-                pre += av[j];
-            }
-            carry_suf += tot[c];
-            const int i0 = c * RN_CHUNK + 4 * lane;
-            const float4 msg4 = make_float4(msg[0], msg[1], msg[2], msg[3]);
-            if (c < NCH - 1 || i0 < L) rn_st_stream4_pol(m_row + i0, msg4, pol_stream);   // rows hold whole quads
-            float *sX = sS + c * RN_CHUNK;   // every chunk has its own scratch: no wait for the previous chunk's readers
-            *reinterpret_cast<float4 *>(sX + 4 * lane) = msg4;
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int i = c * RN_CHUNK + 32 * j + lane;
-                if (c < NCH - 1 || i < L) rn_red_add_pol(a.acc_out + sLin[i], sX[32 * j + lane], pol_keep);
-            }
-        }
+        rn_bp4_ray<NCH, kFirst>(a.acc_in, a.acc_out, kFirst && a.uniform_acc, sLin, sS, sM, m_row, L, lane, pol_stream, pol_keep);
     }
 }
 

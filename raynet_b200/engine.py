@@ -62,7 +62,7 @@ class _Group(object):
 class RayPotentialEngine(object):
     def __init__(self, M, D, n_views, F, H, W, padding, bbox, grid_shape, gamma=0.05, max_rays=0,
                  process_group=None, use_distributed=None, parity=False, memory_budget=None,
-                 max_segment_rays=None, collective="auto"):
+                 max_segment_rays=None, collective="auto", fuse_first_sweep=False):
         """M, D, n_views, F, H, W, padding, bbox, grid_shape: as perform_raynet_fp
         (raynet_fp.py:10-41).  Rows of the per-ray state are padded to rn_row_stride(M) floats.
         max_rays: capacity of the per-ray state on this rank.  memory_budget: bytes of HBM the
@@ -71,13 +71,17 @@ class RayPotentialEngine(object):
         collective: how the per-rank partial accumulators are summed after a sweep when world > 1 --
         "peer": this library's fused exchange kernel over NVLink peer memory (sharding.PeerExchange),
         "nccl": torch.distributed all_reduce, "auto": peer when the GPUs can map each other's memory
-        (float32 accumulators only), else nccl; self.collective says which one runs."""
+        (float32 accumulators only), else nccl; self.collective says which one runs.
+        fuse_first_sweep: score_image() only computes the plane distributions; the FIRST sweep after a reset
+        builds the voxel-space rows inside the sweep kernel (csrc/rn_first.cuh) -- for callers that go
+        front end -> sweeps -> depth (forward_pass, bench); rows are materialised on demand otherwise."""
         M = int(M)
         self.M, self.D, self.V, self.F, self.H, self.W, self.padding = M, D, n_views, F, H, W, padding
         self.grid_shape = tuple(int(g) for g in np.asarray(grid_shape).ravel())
         self.bbox = np.asarray(bbox, dtype=np.float32).ravel()
         self.gamma = float(gamma)
         self.parity = bool(parity)
+        self.fuse_first = bool(fuse_first_sweep) and not self.parity and int(F) == 32
         # float32 prior exactly as np.ones(f32) * (log g - log(1-g)) cast to f32 (mrf_np.py:285-292);
         # parity mode keeps the float64 value like NumPy >= 2 does
         self.prior64 = float(np.log(self.gamma) - np.log(1 - self.gamma))
@@ -130,6 +134,7 @@ class RayPotentialEngine(object):
                     self.collective = "nccl (%s)" % (e,)
         if self._peer is not None:
             # fixed roles: sweeps read `result` and scatter-add into `partial`; the exchange kernel refills `result`
+            # (the partial is double-buffered and cleared by the exchange kernel itself: no fill between sweeps)
             self.acc_prev, self.acc_new = self._peer.result, self._peer.partial
             self.acc_prev.fill_(self.prior)
         else:
@@ -138,6 +143,8 @@ class RayPotentialEngine(object):
         self._acc_uniform = True         # acc_prev holds the prior everywhere (until a sweep or set_accumulator)
         self.axes = torch.zeros((sum(self.grid_shape),), dtype=torch.float32, **kw)
         self._planes = None              # float32 [max_segment_rays, D] plane-distribution scratch of the front end
+        self._planes_all = None          # fuse_first: float32 [resident rays, D] plane distributions of every resident ray
+        self._unmapped = []              # fuse_first: resident segments whose lin / s_hat rows are not built yet
         self._side = None                # side stream + pinned buffer for the class-size read-back
         self._sizes_host = None
         self._pending_sizes = None
@@ -151,11 +158,12 @@ class RayPotentialEngine(object):
         self._axes_set = False
         self.iterations_done = 0
         self.sweep_events = None    # bench.py: list of (start, end) CUDA events around each sweep
+        self.exchange_events = None # bench.py: the same around each exchange (wait for the slowest rank included)
 
     # ------------------------------------------------------------------ memory plan
     def bytes_per_ray(self, resident=True):
         light = 4 * self.R + self.code_stride + 8 + 4 + 4 + 24      # msgs, codes, hdr, count, order, starts / ends
-        return light + (8 * self.R if resident else 0)
+        return light + ((8 * self.R + (4 * self.D if self.fuse_first else 0)) if resident else 0)
 
     def _plan_memory(self, memory_budget):
         n = self.capacity
@@ -177,7 +185,7 @@ class RayPotentialEngine(object):
                 "run fewer reference images per call or more GPUs" %
                 (n, self.M, (light + window + grids) / 1e9, light / 1e9, window / 1e9, grids / 1e9,
                  self.memory_budget / 1e9))
-        self.resident_capacity = int(max(0, (avail - light - window) // (8 * self.R)))
+        self.resident_capacity = int(max(0, (avail - light - window) // (self.bytes_per_ray(True) - self.bytes_per_ray(False))))
 
     # ------------------------------------------------------------------ setup
     def set_voxel_grid(self, voxel_grid):
@@ -212,6 +220,7 @@ class RayPotentialEngine(object):
         self.segments = []
         self.groups = None
         self._scored = {}
+        self._unmapped = []
         self._binned = False
         self._classes_ready = False
         self._pending_sizes = None
@@ -280,11 +289,39 @@ class RayPotentialEngine(object):
     def score_image(self, k, features, P, view_ids=None, n_feature_slots=None):
         """Second half of the front end for segment k of trace_image(): plane-sweep similarity +
         plane->voxel mapping -> s_hat, lin rows.  A streamed segment (see the module docstring) only
-        records its inputs: it is scored into the window at every sweep."""
+        records its inputs: it is scored into the window at every sweep.  With fuse_first_sweep only the
+        plane distributions are computed here; the rows are built by the first sweep (or on demand)."""
         slots = int(n_feature_slots if n_feature_slots is not None else features.shape[0])
         self._scored[k] = (features, P, view_ids, slots)
-        if self.is_resident(k):
-            self._score(k, self.segments[k][0], features, P, view_ids, slots)
+        if not self.is_resident(k):
+            return
+        start, n, _ = self.segments[k]
+        if self.fuse_first and n > 0:
+            if self._planes_all is None:
+                self._planes_all = torch.empty((self.resident_capacity, self.D), dtype=torch.float32, device=self.dev)
+            sl = slice(start, start + n)
+            try:
+                _lib.call("rn_engine_plane_scores", self.params, _ptr(features), _ptr(view_ids) if view_ids is not None else None,
+                          slots, _ptr(P), _ptr(self.starts[sl]), _ptr(self.ends[sl]), _ptr(self._planes_all[sl]), n,
+                          current_stream_ptr())
+                self.launches += 1
+                self._unmapped.append(k)
+                return
+            except NotImplementedError:      # a feature volume the F = 32 kernels cannot address: unfused path
+                self.fuse_first = False
+                self._ensure_mapped()
+        self._score(k, start, features, P, view_ids, slots)
+
+    def _ensure_mapped(self):
+        """Build the lin / s_hat rows of the resident segments that only have plane distributions so far."""
+        for k in self._unmapped:
+            start, n, _ = self.segments[k]
+            sl = slice(start, start + n)
+            _lib.call("rn_engine_map_planes", self.params, _ptr(self.axes), _ptr(self.starts[sl]), _ptr(self.ends[sl]),
+                      _ptr(self.hdr[sl]), _ptr(self.codes[sl]), _ptr(self.count[sl]), _ptr(self._planes_all[sl]),
+                      _ptr(self.s_hat[sl]), _ptr(self.lin[sl]), n, current_stream_ptr())
+            self.launches += 1
+        self._unmapped = []
 
     def _make_groups(self):
         groups, res = [], [k for k in range(len(self.segments)) if self.is_resident(k)]
@@ -365,6 +402,12 @@ class RayPotentialEngine(object):
         self._classes_ready = True
         return self.max_count
 
+    def unit_work(self, unit):
+        """Traversed voxels per `unit` consecutive rays of this rank (float64 device tensor): the weights of the
+        work-balanced block plan of sharding.balanced_boundaries.  n_rays must be a multiple of unit."""
+        c = self.count[:self.n_rays].to(torch.float64)
+        return torch.where(c > 1, c, torch.zeros_like(c)).reshape(-1, int(unit)).sum(dim=1)
+
     # ------------------------------------------------------------------ BP
     def _group_rows(self, g):
         """(lin, s_hat) row tensors of a group: its own rows when resident, else the freshly scored window."""
@@ -379,7 +422,8 @@ class RayPotentialEngine(object):
         if not self._classes_ready:
             self._resolve_classes()
         st = current_stream_ptr()
-        self._fill(self.acc_new, 0.0 if self._peer is not None else sharding.seed_value(self.rank, self.prior))
+        if self._peer is None:
+            self._fill(self.acc_new, sharding.seed_value(self.rank, self.prior))
         if self.sweep_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
@@ -387,8 +431,20 @@ class RayPotentialEngine(object):
         for g in self.groups:
             if g.n == 0:
                 continue
-            lin, s_hat = self._group_rows(g)
             sl = slice(g.start, g.start + g.n)
+            if (g.resident and first and self._acc_uniform and self._unmapped and not self.parity
+                    and sorted(self._unmapped) == list(g.segs)):
+                # mapping fused into the first sweep: the rows are built where they are first used
+                _lib.call("rn_engine_first_sweep_mapped", self.params, _ptr(self.axes), _ptr(self.starts[sl]),
+                          _ptr(self.ends[sl]), _ptr(self.hdr[sl]), _ptr(self.codes[sl]), _ptr(self.count[sl]),
+                          _ptr(self._planes_all[sl]), _ptr(self.lin[sl]), _ptr(self.s_hat[sl]), _ptr(self.msgs[sl]),
+                          _ptr(self.acc_prev), _ptr(self.acc_new), _ptr(self.order[sl]), g.class_offsets, g.n, st)
+                self.launches += int(np.count_nonzero(g.class_sizes))
+                self._unmapped = []
+                continue
+            if g.resident:
+                self._ensure_mapped()
+            lin, s_hat = self._group_rows(g)
             if self.parity:
                 _lib.call("rn_engine_bp_iteration_f64", self.params, _ptr(lin), _ptr(self.count[sl]), _ptr(s_hat),
                           _ptr(self.msgs[sl]), _ptr(self.acc_prev), _ptr(self.acc_new), 1 if first else 0, g.n, st)
@@ -403,8 +459,17 @@ class RayPotentialEngine(object):
             ev[1].record()
             self.sweep_events.append(ev)
         if self._peer is not None:
-            self._peer.allreduce(self.prior)          # acc_prev (= the peer-mapped result buffer) <- prior + sum of partials
+            # acc_prev (= the peer-mapped result buffer) <- prior + sum of partials; the other partial is cleared for
+            # the next sweep and becomes acc_new
+            if self.exchange_events is not None:
+                xe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                xe[0].record()
+            self._peer.allreduce(self.prior)
+            self.acc_new = self._peer.partial
             self.launches += 1
+            if self.exchange_events is not None:
+                xe[1].record()
+                self.exchange_events.append(xe)
         else:
             if self.world > 1:
                 sharding.allreduce_accumulator(self.acc_new, self.pg)
@@ -463,6 +528,7 @@ class RayPotentialEngine(object):
             depth_out = torch.empty((self.n_rays,), dtype=torch.float32, device=self.dev)
         if self.iterations_done == 0:
             self.msgs[:self.n_rays].zero_()
+        self._ensure_mapped()
         for g in self.groups:
             if g.n == 0:
                 continue

@@ -221,6 +221,7 @@ class RayNetForwardPass(ForwardPass):
         self.parity = parity
         self.collective = collective            # exchange step of the multi-GPU path: "auto", "peer" or "nccl" (engine.py)
         self.engine = None
+        self._plans = {}                        # job -> work-balanced block boundaries (shard="rays")
         self._de = None
         self._feat_dev = None
         self._copy_stream = None
@@ -271,7 +272,7 @@ class RayNetForwardPass(ForwardPass):
                                  gamma=gp.gamma_mrf if gp.gamma_mrf is not None else 0.05,
                                  max_rays=n_rays_total, parity=self.parity, memory_budget=self.memory_budget,
                                  max_segment_rays=max_segment, use_distributed=None if self.shard != "none" else False,
-                                 collective=self.collective)
+                                 collective=self.collective, fuse_first_sweep=True)
         eng.set_voxel_grid(vg)
         return eng
 
@@ -324,13 +325,32 @@ class RayNetForwardPass(ForwardPass):
         rays = [self.get_valid_rays_per_image(scene, i) for i in img_ids]
         self.h2d_bytes = self.d2h_bytes = 0
         # ---- this rank's segments: (position in img_ids, first ray, last ray) -------------------
+        plan_key = plan_unit = None
         if by_rays:
-            unit = 64 * H if all(len(r) % (64 * H) == 0 for r in rays) else 8 * H
-            segs = sharding.image_segments([len(r) for r in rays], rank, world, unit)
+            # first call on a job: blocks of equal ray counts; the traversed voxels per group of 8 image columns are
+            # then summed over the ranks and later calls on the same job use blocks of equal WORK
+            # (sharding.balanced_boundaries; rays near the image border cross few voxels)
+            lens = [len(r) for r in rays]
+            plan_unit = 8 * H if all(n % (8 * H) == 0 for n in lens) else 0
+            plan_key = (id(scene), images_range, world, tuple(lens))
+            bounds = self._plans.get(plan_key)
+            if bounds is not None:
+                all_segs = [sharding.segments_from_unit_boundaries(lens, plan_unit, bounds[r], bounds[r + 1])
+                            for r in range(world)]
+            else:
+                unit = 64 * H if all(n % (64 * H) == 0 for n in lens) else 8 * H
+                all_segs = [sharding.image_segments(lens, r, world, unit) for r in range(world)]
+            segs = all_segs[rank]
+            # the same on every rank, so that every rank decides alike whether the engine has to grow (its
+            # construction is collective: peer-mapped accumulators)
+            total_cap = max(sum(b - a for (_, a, b) in sg) for sg in all_segs)
         else:
             segs = [(k, 0, len(r)) for k, r in enumerate(rays)]
+            total_cap = int(sum(b - a for (_, a, b) in segs))
         total = int(sum(b - a for (_, a, b) in segs))
         max_seg = max([b - a for (_, a, b) in segs] + [1])
+        if by_rays:
+            max_seg = max(max([b - a for (_, a, b) in sg] + [1]) for sg in all_segs)
         # ---- features: once per distinct view ---------------------------------------------------
         orders_all = self._view_orders(scene, img_ids)
         views = sorted(set(v for (k, _, _) in segs for v in orders_all[k]))
@@ -396,9 +416,9 @@ class RayNetForwardPass(ForwardPass):
                         copied[k].record()
                 self.h2d_bytes += f_host.numel() * 4
         F = int(self._feat_dev.shape[-1])
-        if self.engine is None or self.engine.capacity < total or self.engine.max_segment_rays < min(max_seg, total):
+        if self.engine is None or self.engine.capacity < total_cap or self.engine.max_segment_rays < min(max_seg, total_cap):
             self.engine = None                     # release the old state before the larger one is allocated
-            self.engine = self._make_engine(scene, F, total, max_seg)
+            self.engine = self._make_engine(scene, F, total_cap, max_seg)
         else:
             self.engine.reset()
         # ---- front end, first half: trace the rays of every segment, bin them --------------------
@@ -428,6 +448,15 @@ class RayNetForwardPass(ForwardPass):
             per_seg.append((meta_dev[j, :nP], vids_dev[j]))
         self.engine.finalize_frontend()
         self.d2h_bytes += 4
+        if by_rays and plan_unit and plan_key not in self._plans:
+            n_units = int(sum(lens)) // plan_unit
+            work = torch.zeros((n_units,), dtype=torch.float64, device=dev)
+            if total:
+                offs0 = np.concatenate([[0], np.cumsum(lens)])
+                lo_u = int(offs0[segs[0][0]] + segs[0][1]) // plan_unit
+                work[lo_u:lo_u + total // plan_unit] = self.engine.unit_work(plan_unit)
+            dist.all_reduce(work, op=dist.ReduceOp.SUM)
+            self._plans[plan_key] = sharding.balanced_boundaries(work.cpu().numpy(), world)
         # ---- front end, second half: similarity + plane->voxel mapping per segment ----------------
         for j, (P_dev, view_ids) in enumerate(per_seg):
             for v in orders_all[segs[j][0]]:

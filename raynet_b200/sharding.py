@@ -63,6 +63,42 @@ def image_segments(rays_per_image, rank, world, unit=1):
     return out
 
 
+def balanced_boundaries(unit_weights, world):
+    """Cut a sequence of work units (weights >= 0: e.g. traversed voxels per group of 8 image columns) into `world`
+    contiguous blocks of (nearly) equal total weight.  Returns world + 1 non-decreasing unit indices, first 0, last
+    len(unit_weights).  Deterministic: every rank computes the same plan from the same weights."""
+    import numpy as np
+    w = np.asarray(unit_weights, dtype=np.float64)
+    n = int(w.shape[0])
+    world = int(world)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    total = cum[-1]
+    if total <= 0:
+        return [ray_block(n, r, world)[0] for r in range(world)] + [n]
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = int(np.searchsorted(cum, target, side="left"))
+        if k > 0 and abs(cum[k - 1] - target) <= abs(cum[min(k, n)] - target):
+            k -= 1                                  # the nearer of the two neighbouring cuts
+        bounds.append(min(max(k, bounds[-1]), n))
+    bounds.append(n)
+    return bounds
+
+
+def segments_from_unit_boundaries(rays_per_image, unit, lo_unit, hi_unit):
+    """[(image_position, first, last_exclusive), ...] of the units [lo_unit, hi_unit) of the job's ray enumeration
+    (every image a whole number of `unit` rays)."""
+    out, off = [], 0
+    start, stop = int(lo_unit) * int(unit), int(hi_unit) * int(unit)
+    for k, n in enumerate(rays_per_image):
+        a, b = max(start, off), min(stop, off + n)
+        if b > a:
+            out.append((k, a - off, b - off))
+        off += n
+    return out
+
+
 def images_of_rank(n_images, rank, world):
     """Weak-scaling layout: whole reference images dealt out in contiguous runs."""
     start, stop = ray_block(n_images, rank, world)
@@ -87,8 +123,10 @@ class PeerExchange(object):
     """Peer-mapped partial / result accumulators of one rank + the fused exchange kernel.
 
         ex = PeerExchange(n_elements, device, group)      # collective: every rank of the group constructs it
-        ex.partial   float32 [n]   this rank's sweep scatter-adds into it (zero it before every sweep)
+        ex.partial   float32 [n]   the partial this rank's CURRENT sweep scatter-adds into (already zero)
         ex.result    float32 [n]   after ex.allreduce(prior): prior + sum over ranks of partial, on every rank
+    The partials are double-buffered: allreduce() also clears the one the next sweep will use and flips
+    `ex.partial` to it, so no fill is launched between sweeps; reset() zeroes the current one.
     Raises RuntimeError when the GPUs cannot map each other's memory (the caller then stays on NCCL)."""
 
     def __init__(self, n, device, group=None, n_ctas=None):
@@ -105,21 +143,31 @@ class PeerExchange(object):
         sms = torch.cuda.get_device_properties(device).multi_processor_count
         self.n_ctas = int(n_ctas or sms)
         try:
-            self.partial = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+            self._partials = [symm_mem.empty(self.n, dtype=torch.float32, device=device) for _ in range(2)]
             self.result = symm_mem.empty(self.n, dtype=torch.float32, device=device)
             self.flags = symm_mem.empty(self.n_ctas * self.world, dtype=torch.int32, device=device)
             self.flags.zero_()
-            handles = [symm_mem.rendezvous(t, group.group_name) for t in (self.partial, self.result, self.flags)]
+            for t in self._partials:
+                t.zero_()
+            handles = [symm_mem.rendezvous(t, group.group_name) for t in self._partials + [self.result, self.flags]]
         except Exception as e:      # no NVLink / P2P mapping between these devices
             raise RuntimeError("peer-mapped accumulators unavailable: %r" % (e,))
         self._handles = handles     # keep the mappings alive
         self._tables = [(ctypes.c_uint64 * self.world)(*[int(p) for p in h.buffer_ptrs]) for h in handles]
+        self.cur = 0
         self.epoch = 0
         torch.cuda.synchronize(device)
-        dist.barrier(group)         # every rank's flags are zeroed before anyone signals
+        dist.barrier(group)         # every rank's flags and partials are zeroed before anyone signals
+
+    @property
+    def partial(self):
+        return self._partials[self.cur]
 
     def allreduce(self, prior):
-        self._lib.call("rn_peer_allreduce_f32", self._tables[0], self._tables[1], self._tables[2], self.rank, self.world,
-                       self.n_ctas, ctypes.c_uint32(self.epoch & 0xffffffff), float(prior), self.n, self._stream())
+        nxt = self.cur ^ 1
+        self._lib.call("rn_peer_allreduce_f32", self._tables[self.cur], self._tables[2], self._tables[3],
+                       self._partials[nxt].data_ptr(), self.rank, self.world, self.n_ctas,
+                       ctypes.c_uint32(self.epoch & 0xffffffff), float(prior), self.n, self._stream())
         self.epoch += 2
+        self.cur = nxt
         return self.result

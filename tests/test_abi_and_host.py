@@ -105,6 +105,17 @@ def test_ray_blocks_partition():
             assert pieces[0][0] == 0 and pieces[-1][1] == H * H
             assert all(pieces[i][1] == pieces[i + 1][0] for i in range(len(pieces) - 1))
     assert sharding.aligned_ray_block(1000, 1, 3, 64) == sharding.ray_block(1000, 1, 3)      # not a multiple: unit 1
+    # work-balanced cuts: equal total weight per block up to one unit, monotone, deterministic
+    rng = np.random.RandomState(0)
+    w = rng.rand(576) ** 3 + np.linspace(0, 2, 576)
+    for world in (1, 2, 4, 8, 5):
+        b = sharding.balanced_boundaries(w, world)
+        assert b[0] == 0 and b[-1] == 576 and len(b) == world + 1 and all(b[i] <= b[i + 1] for i in range(world))
+        work = np.array([w[b[i]:b[i + 1]].sum() for i in range(world)])
+        assert work.max() - work.min() <= 2 * w.max() + 1e-9
+    assert sharding.balanced_boundaries(np.zeros(10), 3) == [0, 4, 7, 10]
+    segs = sharding.segments_from_unit_boundaries([64, 64, 64], 8, 5, 19)
+    assert segs == [(0, 40, 64), (1, 0, 64), (2, 0, 24)]
     assert sharding.image_segments([100, 64], 0, 2, 64) == sharding.image_segments([100, 64], 0, 2, 1)
     assert sharding.seed_value(0, -2.5) == -2.5 and sharding.seed_value(3, -2.5) == 0.0
 

@@ -421,12 +421,12 @@ def _assert_depth_matches(depth, ref_depth, ref_Snew, gap=1e-5):
 
 
 # ----------------------------------------------------------------------------- resident engine, end to end
-def _run_engine(torch, c, iters, refs=None, parity=False, memory_budget=None, splits=None):
+def _run_engine(torch, c, iters, refs=None, parity=False, memory_budget=None, splits=None, fuse=False):
     """splits: cut every image's ray list at these fractions into separate segments (partial images)."""
     from raynet_b200.engine import RayPotentialEngine
     refs = refs if refs is not None else [c.ref_idx]
     eng = RayPotentialEngine(c.M, c.D, c.V, 32, c.H, c.W, 11, c.bbox, c.grid, max_rays=c.N * len(refs),
-                             use_distributed=False, parity=parity, memory_budget=memory_budget)
+                             use_distributed=False, parity=parity, memory_budget=memory_budget, fuse_first_sweep=fuse)
     eng.set_voxel_grid(c.vgrid)
     feats = _d(torch, c.features_all)
     for ref in refs:
@@ -495,6 +495,31 @@ def test_engine_end_to_end_vs_oracle(torch_cuda, oracle, mk, iters, parity_log):
             n0 += n
         del eng
     parity_log["engine_end_to_end/%s/%d_sweeps" % (mk.__name__, iters)] = rec
+
+
+@pytest.mark.parametrize("mk,iters", [(case_c1, 3), (case_small, 2), (case_long, 1), (case_xlong, 2)])
+def test_fused_first_sweep_equals_separate_mapping(torch_cuda, mk, iters):
+    """rn_engine_first_sweep_mapped (rows built inside the first sweep kernel) against rn_engine_similarity +
+    rn_engine_bp_iteration: the same arithmetic, so identical rows and, up to the order of the float atomics,
+    identical messages and accumulators; rays BP skips still get their rows; depth-only use materialises them."""
+    torch = torch_cuda
+    c = mk()
+    refs = list(range(min(c.V, 3)))
+    a = _run_engine(torch, c, iters, refs)
+    b = _run_engine(torch, c, iters, refs, fuse=True)
+    assert b.fuse_first and not b._unmapped
+    n = a.n_rays
+    cnt = a.count[:n]
+    live = torch.arange(a.R, device="cuda")[None, :] < cnt[:, None]
+    assert torch.equal(torch.where(live, a.lin[:n], 0), torch.where(live, b.lin[:n], 0))
+    assert torch.equal(torch.where(live, a.s_hat[:n], 0), torch.where(live, b.s_hat[:n], 0))
+    assert float((a.messages() - b.messages()).abs().max()) <= 2e-5
+    assert float((a.occupancy() - b.occupancy()).abs().max()) <= 2e-6
+    da, db = a.depth(), b.depth()
+    assert float(((da - db).abs() > 1e-6).float().mean()) < 1e-3
+    z = _run_engine(torch, c, 0, refs, fuse=True)          # no sweep at all: depth() builds the rows on demand
+    z0 = _run_engine(torch, c, 0, refs)
+    assert torch.equal(z.depth(), z0.depth())
 
 
 def test_partial_segments_and_streaming_equal_whole_images(torch_cuda):

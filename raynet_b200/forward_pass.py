@@ -360,12 +360,12 @@ class RayNetForwardPass(ForwardPass):
         first_use = []
         for (k, _, _) in segs:
             first_use += [slot[v] for v in orders_all[k] if slot[v] not in first_use]
-        if by_rays and hasattr(self._model, "predict_features") and len(views) > 0:
-            # every rank needs (nearly) every view: deal the views out, run the model on this rank's share,
-            # exchange the maps with one all-gather (equal chunks of `per` view slots per rank)
+        if by_rays and hasattr(self._model, "predict_features"):      # (collective: ranks without rays take part too)
+            # every rank needs (nearly) every view: the views are dealt out round-robin (view j * world + r to rank r),
+            # every rank runs the model on its share, and the maps are exchanged over NVLink: one all-gather per full
+            # round of `world` views (equal chunks, no padding), broadcasts for the views of the last partial round
             all_views = sorted(set(v for o in orders_all for v in o))
-            per = -(-len(all_views) // world)
-            mine = all_views[rank * per:(rank + 1) * per]
+            mine = all_views[rank::world]
             part = self._predict_views(scene, mine) if mine else None
             fshape = self._staging.get("feat_shape")
             if fshape is None:                   # ranks without a view learn the map shape from the others, once
@@ -373,13 +373,17 @@ class RayNetForwardPass(ForwardPass):
                 dist.all_gather_object(shapes, tuple(part.shape[1:]) if part is not None else None)
                 fshape = [s for s in shapes if s is not None][0]
                 self._staging["feat_shape"] = fshape
-            if self._feat_dev is None or tuple(self._feat_dev.shape) != (world * per,) + tuple(fshape):
-                self._feat_dev = torch.empty((world * per,) + tuple(fshape), dtype=torch.float32, device=dev)
-            if part is not None:
-                self._feat_dev[rank * per:rank * per + len(mine)].copy_(part.to(dev, non_blocking=True))
-            dist.all_gather_into_tensor(self._feat_dev, self._feat_dev[rank * per:(rank + 1) * per])
+            n_slots = len(all_views)
+            if self._feat_dev is None or tuple(self._feat_dev.shape) != (n_slots,) + tuple(fshape):
+                self._feat_dev = torch.empty((n_slots,) + tuple(fshape), dtype=torch.float32, device=dev)
+            for j in range(len(mine)):
+                self._feat_dev[j * world + rank].copy_(part[j].to(dev, non_blocking=True))
+            full = n_slots // world
+            for j in range(full):
+                dist.all_gather_into_tensor(self._feat_dev[j * world:(j + 1) * world], self._feat_dev[j * world + rank])
+            for v in range(full * world, n_slots):
+                dist.broadcast(self._feat_dev[v], src=v - full * world)
             slot = dict((v, k) for k, v in enumerate(all_views))
-            n_slots = world * per
         else:
             # a model that works on the device (raynet_b200.models.SimpleCNN) runs on the side stream: its image
             # upload and convolutions overlap with the tracing and binning of the rays, which need no features

@@ -51,8 +51,14 @@ class ForwardPass(object):
         return np.minimum(D, truncate)
 
     def get_valid_rays_per_image(self, scene, i):
-        """forward_pass.py:168-179."""
+        """forward_pass.py:168-179 (the all-pixels index list is built once per image size and shared, read-only)."""
         H, W = scene.image_shape
+        if not self._filter_out_rays:
+            cached = getattr(self, "_all_pixels", None)
+            if cached is None or cached.shape[0] != H * W:
+                cached = self._all_pixels = np.arange(H * W, dtype=np.int32)
+                cached.setflags(write=False)
+            return cached
         idxs = np.arange(H * W, dtype=np.int32)
         if self._filter_out_rays:
             idxs = idxs.reshape(W, H).T

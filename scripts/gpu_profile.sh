@@ -14,7 +14,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     --csv --log-file gpurun_out/bp_sweep_dram_${CFG}_${TAG}.csv $B > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:bp4_kernel<\(int\)4, \(bool\)0>' -s 1 -c 1 -f \
     -o gpurun_out/prof_bp4_${CFG}_${TAG} $B > gpurun_out/prof_bp4_${CFG}_${TAG}.log 2>&1
-for K in ${KERNELS:-simscore3_kernel planemap3_kernel depth3_kernel dda_codes_kernel}; do
+for K in ${KERNELS:-simscore3_kernel bp4_first_mapped_kernel depth3_kernel dda_codes_kernel}; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 1 -f \
       -o gpurun_out/prof_${K}_${CFG}_${TAG} $B > gpurun_out/prof_${K}_${CFG}_${TAG}.log 2>&1
 done

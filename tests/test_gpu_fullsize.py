@@ -202,3 +202,67 @@ def test_fullsize_rerun_agrees(torch_cuda, run):
         eng.run_bp(2)
         res.append(eng.occupancy().clone())
     assert float((res[0] - res[1]).abs().max()) <= 2e-6
+
+
+def test_c2_whole_workload_end_to_end_vs_oracle(torch_cuda, oracle, parity_log):
+    """BASELINE.json configs[1] (C2: 128^3 grid, 5 views, 32 planes, 5 x 256 x 256 = 327 680 rays, 3 sweeps) from
+    images' features to occupancy, WHOLE workload against the CPU oracle run the same way (OpenMP, a few seconds):
+    every voxel list bit-exact, every voxel of sigma(acc) after all 3 sweeps within 1e-5 of the float64 flavour of
+    the reference -- in parity mode and in the fast mode -- and the depth maps equal wherever the arg-max is decided."""
+    torch = torch_cuda
+    import bench
+    from raynet_b200.engine import RayPotentialEngine
+    r = FullRun(torch, "c2")
+    cfg = r.cfg
+    H, W, M, I = cfg["H"], cfg["W"], cfg["M"], cfg["I"]
+    HW = H * W
+    ids = np.arange(HW, dtype=np.int32)
+    fronts = [r.oracle_frontend(oracle, k, ids) for k in range(len(r.images))]
+    idx = np.concatenate([f["idx"] for f in fronts])
+    cnt = np.concatenate([f["cnt"] for f in fronts])
+    S_vox = np.concatenate([f["S_vox"] for f in fronts])
+    acc64, msgs64 = oracle.belief_propagation(S_vox, idx, cnt, r.grid, gamma=GAMMA, bp_iterations=I, acc_f64=True)
+    occ64 = oracle.occupancy(acc64)
+    acc32, _ = oracle.belief_propagation(S_vox, idx, cnt, r.grid, gamma=GAMMA, bp_iterations=I, acc_f64=False)
+    flav = float(np.abs(oracle.occupancy(acc32) - occ64).max())
+    S_new = oracle.depth_distribution(S_vox, idx, cnt, r.grid, acc64, msgs64, acc_f64=True)
+    vgrid = oracle.voxel_grid(r.bbox, r.grid)
+    assert np.array_equal(r.eng.count[:r.eng.n_rays].cpu().numpy(), cnt)
+    for a in range(0, len(cnt), 65536):
+        assert np.array_equal(r.eng.voxel_indices(start=a, n=min(65536, len(cnt) - a)).cpu().numpy(), idx[a:a + 65536])
+    rec = {"rays": int(len(cnt)), "reference_f32_vs_f64_flavour": flav}
+    dev = torch.device("cuda")
+    for parity in (False, True):
+        if parity:
+            del r.eng
+            torch.cuda.empty_cache()
+            eng = RayPotentialEngine(M, cfg["D"], cfg["V"], bench.F, H, W, bench.PADDING, r.bbox, tuple(r.grid), gamma=GAMMA,
+                                     max_rays=len(cnt), use_distributed=False, parity=True)
+            eng.set_voxel_grid(r.scene.voxel_grid())
+            slot = dict((v, k) for k, v in enumerate(r.views))
+            pix = torch.arange(HW, dtype=torch.int32, device=dev)
+            for (order, P, P_inv, centre) in r.cams:
+                eng.add_image(pix, r.feats_dev, torch.from_numpy(P).to(dev), torch.from_numpy(P_inv).to(dev),
+                              torch.from_numpy(centre).to(dev),
+                              view_ids=torch.tensor([slot[v] for v in order], dtype=torch.int32, device=dev),
+                              n_feature_slots=len(r.views))
+            eng.finalize_frontend()
+        else:
+            eng = r.eng
+        eng.run_bp(I)
+        err = float(np.abs(eng.occupancy().cpu().numpy() - occ64).max())
+        depth = eng.depth().cpu().numpy()
+        agree = []
+        for k, f in enumerate(fronts):
+            sl = slice(k * HW, (k + 1) * HW)
+            ref_depth, _ = oracle.argmax_depth(S_new[sl], f["idx"], vgrid, r.grid, r.cams[k][3])
+            top2 = -np.sort(-S_new[sl], axis=1)[:, :2]
+            decided = (top2[:, 0] - top2[:, 1]) > 1e-5
+            assert np.abs(depth[sl][decided] - ref_depth[decided]).max() < 1e-6
+            agree.append(float((np.abs(depth[sl] - ref_depth) < 1e-6).mean()))
+        rec["parity" if parity else "fast"] = {"occupancy": err, "depth_maps_equal_fraction": float(np.mean(agree))}
+        print("C2 whole workload, %s: max |occ - f64 ref| over %d voxels = %.2e (f32 ref vs f64 ref %.2e), depth equal %.5f"
+              % ("parity" if parity else "fast", occ64.size, err, flav, np.mean(agree)))
+        assert err <= TOL_P, (parity, err)
+        assert np.mean(agree) > 0.999
+    parity_log["c2_whole_workload/3_sweeps"] = rec

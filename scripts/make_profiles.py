@@ -72,7 +72,7 @@ shutil.copy(os.path.join(G, "bp_sweep_dram_%s_%s.csv" % (cfg, tag)), os.path.joi
 
 # 3. full-set summaries
 reps = [os.path.join(G, f) for f in ["prof_bp4_%s_%s.ncu-rep" % (cfg, tag)] +
-        ["prof_%s_%s_%s.ncu-rep" % (k, cfg, tag) for k in ("simscore3_kernel", "planemap3_kernel", "depth3_kernel", "dda_codes_kernel")]
+        ["prof_%s_%s_%s.ncu-rep" % (k, cfg, tag) for k in ("simscore3_kernel", "bp4_first_mapped_kernel", "planemap3_kernel", "depth3_kernel", "dda_codes_kernel")]
         if os.path.exists(os.path.join(G, f))]
 out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py")] + reps, capture_output=True, text=True).stdout
 open(os.path.join(P, "%s_ncu_full_%s.txt" % (tag, cfg)), "w").write(out)

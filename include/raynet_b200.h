@@ -408,6 +408,22 @@ int rn_engine_first_sweep_mapped(const RnParams *p, const float *axis_centres, c
                                  float *acc_out, const int32_t *order, const int64_t *class_offsets, int64_t n_rays,
                                  void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * MV-CNN on the tensor cores (csrc/rn_cnn_tc.cuh): the 32 -> 32 channel layers as an implicit-GEMM convolution on
+ * tcgen05.mma kind::tf32 with 3 x TF32 split products (float32-level accuracy).  Activations travel between the
+ * layers as exact pairs x = hi + lo (hi: low 13 mantissa bits cleared); w_cat float32 [9][64][32]: per tap the rows
+ * 0..31 hold the hi part of W[tap][cout][cin], the rows 32..63 its lo part.  rn_conv3x3_bn_relu_split = the
+ * CUDA-core layer (rn_conv3x3_bn_relu, e.g. the 3 -> 32 first layer) with a hi / lo epilogue; rn_conv3x3_bn_relu_tc
+ * with out_lo == NULL writes the plain float32 result (last layer).  Replaces models.py:90-111 / model.predict
+ * (forward_pass.py:622-624) like rn_conv3x3_bn_relu.
+ * ------------------------------------------------------------------------------------- */
+int rn_conv3x3_bn_relu_split(const float *in, const float *weights, const float *scale, const float *shift, float *out_hi,
+                             float *out_lo, int32_t n_images, int32_t height, int32_t width, int32_t channels_in,
+                             int32_t relu, void *stream);
+int rn_conv3x3_bn_relu_tc(const float *in_hi, const float *in_lo, const float *w_cat, const float *scale, const float *shift,
+                          float *out_hi, float *out_lo, int32_t n_images, int32_t height, int32_t width, int32_t relu,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

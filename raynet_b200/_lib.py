@@ -101,6 +101,9 @@ SIGNATURES = {
     "rn_engine_plane_scores": [_PP, _PTR, _PTR, _I32] + [_PTR] * 4 + [_I64, _PTR],
     "rn_engine_map_planes": [_PP] + [_PTR] * 9 + [_I64, _PTR],
     "rn_engine_first_sweep_mapped": [_PP] + [_PTR] * 14 + [_I64, _PTR],
+    # MV-CNN on the tensor cores
+    "rn_conv3x3_bn_relu_split": [_PTR] * 6 + [_I32] * 5 + [_PTR],
+    "rn_conv3x3_bn_relu_tc": [_PTR] * 7 + [_I32] * 4 + [_PTR],
     # exchange step over NVLink peer memory
     "rn_peer_allreduce_f32": [_PTR, _PTR, _PTR, _PTR, _I32, _I32, _I32, ctypes.c_uint32, ctypes.c_float, _I64, _PTR],
 }

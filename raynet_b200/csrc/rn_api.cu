@@ -13,6 +13,7 @@
 #include "rn_simmap3.cuh"
 #include "rn_first.cuh"
 #include "rn_cnn.cuh"
+#include "rn_cnn_tc.cuh"
 #include "rn_fusion.cuh"
 
 namespace {
@@ -485,7 +486,7 @@ int rn_conv3x3_bn_relu(const float *in, const float *weights, const float *scale
     if (height < 3 || width < 3) return fail(RN_ERR_SHAPE, "conv3x3 needs images of at least 3 x 3 pixels");
     if (!in || !weights || !scale || !shift || !out) return fail(RN_ERR_SHAPE, "conv3x3: NULL buffer");
     if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return fail(RN_ERR_SHAPE, "conv3x3: output must be 16-byte aligned");
-    ConvArgs a = {in, weights, scale, shift, out, n_images, height, width, relu};
+    ConvArgs a = {in, weights, scale, shift, out, n_images, height, width, relu, nullptr};
     switch (channels_in) {
         case 1: return launch_conv3x3<1>(a, S(stream));
         case 3: return launch_conv3x3<3>(a, S(stream));
@@ -1113,6 +1114,44 @@ int rn_engine_first_sweep_mapped(const RnParams *p, const float *axis_centres, c
         if (rc) return rc;
     }
     return RN_OK;
+}
+
+// ---- MV-CNN on the tensor cores (rn_cnn_tc.cuh) --------------------------------------------------------------------
+int rn_conv3x3_bn_relu_split(const float *in, const float *weights, const float *scale, const float *shift, float *out_hi,
+                             float *out_lo, int32_t n_images, int32_t height, int32_t width, int32_t channels_in,
+                             int32_t relu, void *stream) {
+    if (n_images <= 0) return RN_OK;
+    if (height < 3 || width < 3) return fail(RN_ERR_SHAPE, "conv3x3 needs images of at least 3 x 3 pixels");
+    if (!in || !weights || !scale || !shift || !out_hi || !out_lo) return fail(RN_ERR_SHAPE, "conv3x3: NULL buffer");
+    ConvArgs a = {in, weights, scale, shift, out_hi, n_images, height, width, relu, out_lo};
+    switch (channels_in) {
+        case 1: return launch_conv3x3<1>(a, S(stream));
+        case 3: return launch_conv3x3<3>(a, S(stream));
+        case 32: return launch_conv3x3<32>(a, S(stream));
+    }
+    return fail(RN_ERR_UNSUPPORTED, "conv3x3: %d input channels (supported: 1, 3, 32)", channels_in);
+}
+
+int rn_conv3x3_bn_relu_tc(const float *in_hi, const float *in_lo, const float *w_cat, const float *scale, const float *shift,
+                          float *out_hi, float *out_lo, int32_t n_images, int32_t height, int32_t width, int32_t relu,
+                          void *stream) {
+    if (n_images <= 0) return RN_OK;
+    if (height < 3 || width < 3) return fail(RN_ERR_SHAPE, "conv3x3 needs images of at least 3 x 3 pixels");
+    if (!in_hi || !in_lo || !w_cat || !scale || !shift || !out_hi) return fail(RN_ERR_SHAPE, "conv3x3_tc: NULL buffer");
+    if (((reinterpret_cast<uintptr_t>(in_hi) | reinterpret_cast<uintptr_t>(in_lo) | reinterpret_cast<uintptr_t>(out_hi) |
+          reinterpret_cast<uintptr_t>(out_lo) | reinterpret_cast<uintptr_t>(w_cat)) & 15) != 0)
+        return fail(RN_ERR_SHAPE, "conv3x3_tc: buffers must be 16-byte aligned");
+    static SmemOptIn opt;
+    if (int rc = opt.ensure(conv3x3_tc_kernel, RN_TC_SMEM_BYTES, "conv3x3_tc_kernel")) return rc;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail(RN_ERR_CUDA, "conv3x3_tc setup: %s", cudaGetErrorString(e));
+    ConvTcArgs a = {in_hi, in_lo, w_cat, scale, shift, out_hi, out_lo, n_images, height, width, relu};
+    const int ho = height - 2, wo = width - 2;
+    const int64_t units = (int64_t)n_images * ((wo + RN_TC_PX - 1) / RN_TC_PX) * ((ho + RN_TC_CHUNK_ROWS - 1) / RN_TC_CHUNK_ROWS);
+    conv3x3_tc_kernel<<<(unsigned)(units < sms ? units : sms), 192, RN_TC_SMEM_BYTES, S(stream)>>>(a);
+    return check_launch("conv3x3_tc_kernel");
 }
 
 }  // extern "C"

@@ -53,6 +53,7 @@ struct ConvArgs {
     const float *shift;    // [32]
     float *out;            // [N][Hi-2][Wi-2][32]
     int n, hi, wi, relu;
+    float *out_lo;         // optional: out receives the TF32-exact high part of the result, out_lo the rest (rn_cnn_tc.cuh)
 };
 
 template <int CIN>
@@ -163,6 +164,18 @@ __global__ void __launch_bounds__(128) conv3x3_kernel(ConvArgs a) {
                     for (int q = 0; q < 8; q++) {
                         r[q] = fmaf(acc[i][q], sc[q], sh[q]);
                         if (a.relu) r[q] = fmaxf(r[q], 0.f);
+                    }
+                    if (a.out_lo) {   // hi / lo pair for the tensor-core layers: hi exactly representable in TF32
+                        float l[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float h = __uint_as_float(__float_as_uint(r[q]) & 0xffffe000u);
+                            l[q] = r[q] - h;
+                            r[q] = h;
+                        }
+                        float4 *l4 = reinterpret_cast<float4 *>(a.out_lo + (dst - a.out) + (int64_t)ox * RN_CNN_COUT);
+                        l4[0] = make_float4(l[0], l[1], l[2], l[3]);
+                        l4[1] = make_float4(l[4], l[5], l[6], l[7]);
                     }
                     float4 *d4 = reinterpret_cast<float4 *>(dst + (int64_t)ox * RN_CNN_COUT);
                     d4[0] = make_float4(r[0], r[1], r[2], r[3]);

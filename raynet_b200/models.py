@@ -9,8 +9,12 @@ Mirror of the reference's `create_simple_cnn` (raynet/models.py:90-111): five
 hook of RayNetForwardPass that leaves the feature volume ON THE DEVICE (no 316 MB host round trip
 per call on the headline configuration).
 
-Compute: raynet_b200/csrc/rn_cnn.cuh through `rn_conv3x3_bn_relu` (one launch per layer).  There is
-no CPU fallback; weights come from `set_weights` in the Keras order (kernel, bias, gamma, beta,
+Compute (one launch per layer, two code paths selected by `tensor_cores`):
+  * raynet_b200/csrc/rn_cnn.cuh through `rn_conv3x3_bn_relu`: direct convolution in fp32 on the CUDA cores;
+  * raynet_b200/csrc/rn_cnn_tc.cuh through `rn_conv3x3_bn_relu_tc` (the four 32 -> 32 layers; the 3 -> 32 first
+    layer stays on the CUDA cores with a hi / lo epilogue, `rn_conv3x3_bn_relu_split`): implicit-GEMM convolution on
+    tcgen05.mma kind::tf32 with 3 x TF32 split products -- float32-level accuracy on the tensor cores.
+There is no CPU fallback; weights come from `set_weights` in the Keras order (kernel, bias, gamma, beta,
 moving_mean, moving_variance per layer) or from `random_init` (no checkpoints are available offline).
 """
 import numpy as np
@@ -26,9 +30,10 @@ class SimpleCNN(object):
     n_layers = 5
     filters = 32
 
-    def __init__(self, channels=3, epsilon=BN_EPSILON):
+    def __init__(self, channels=3, epsilon=BN_EPSILON, tensor_cores=True):
         self.channels = int(channels)
         self.epsilon = float(epsilon)
+        self.tensor_cores = bool(tensor_cores)      # 32 -> 32 layers on tcgen05 (3 x TF32) instead of the CUDA cores
         self._layers = None       # list of dict(kernel, bias, gamma, beta, mean, var) numpy float32
         self._dev = None          # list of (kernel, scale, shift) CUDA tensors
         self.launches = 0
@@ -39,11 +44,11 @@ class SimpleCNN(object):
 
     # ------------------------------------------------------------------ weights
     @classmethod
-    def random_init(cls, channels=3, seed=0, trained_like=True):
+    def random_init(cls, channels=3, seed=0, trained_like=True, tensor_cores=True):
         """Glorot-uniform kernels (Keras default); with trained_like=True the batch-norm statistics and
         biases are random too, so that every term of the folded affine map is exercised."""
         rng = np.random.default_rng(seed)
-        m = cls(channels)
+        m = cls(channels, tensor_cores=tensor_cores)
         weights = []
         cin = m.channels
         for _ in range(cls.n_layers):
@@ -86,9 +91,17 @@ class SimpleCNN(object):
             for L in self._layers:
                 scale = L["gamma"].astype(np.float64) / np.sqrt(L["var"].astype(np.float64) + self.epsilon)
                 shift = L["beta"].astype(np.float64) + scale * (L["bias"].astype(np.float64) - L["mean"].astype(np.float64))
-                self._dev.append((torch.from_numpy(np.ascontiguousarray(L["kernel"])).to(dev),
-                                  torch.from_numpy(scale.astype(np.float32)).to(dev),
-                                  torch.from_numpy(shift.astype(np.float32)).to(dev)))
+                k = np.ascontiguousarray(L["kernel"])
+                w_cat = None
+                if k.shape[2] == self.filters:
+                    # tensor-core layers: per tap [cout][cin] (K-major), split into an exactly-TF32 high part (low 13
+                    # mantissa bits cleared) and the float32 remainder, stacked as 64 rows per tap (rn_cnn_tc.cuh)
+                    w = np.ascontiguousarray(k.transpose(0, 1, 3, 2).reshape(9, self.filters, self.filters))
+                    hi = (w.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+                    lo = (w - hi).astype(np.float32)
+                    w_cat = torch.from_numpy(np.ascontiguousarray(np.concatenate([hi, lo], axis=1))).to(dev)
+                self._dev.append((torch.from_numpy(k).to(dev), torch.from_numpy(scale.astype(np.float32)).to(dev),
+                                  torch.from_numpy(shift.astype(np.float32)).to(dev), w_cat))
         return self._dev
 
     # ------------------------------------------------------------------ inference
@@ -100,22 +113,40 @@ class SimpleCNN(object):
         if h < 2 * self.n_layers + 1 or w < 2 * self.n_layers + 1:
             raise AssertionError("input of %d x %d pixels is too small for five valid 3x3 convolutions" % (h, w))
         cin = self.channels
-        # intermediate layers ping-pong between two cached buffers (the first layer's output is the
-        # largest); only the returned feature volume is a fresh tensor
+        st = current_stream_ptr()
+        # intermediate layers ping-pong between cached buffers (the first layer's output is the largest; the
+        # tensor-core path keeps every intermediate as a hi / lo pair); only the returned feature volume is a fresh tensor
         need = n * (h - 2) * (w - 2) * self.filters
-        if self._scratch is None or self._scratch[0].numel() < need or self._scratch[0].device != x.device:
-            self._scratch = [torch.empty((need,), dtype=torch.float32, device=x.device) for _ in range(2)]
-        for l, (k, scale, shift) in enumerate(self._device_weights()):
+        n_scratch = 4 if self.tensor_cores else 2
+        if (self._scratch is None or len(self._scratch) != n_scratch or self._scratch[0].numel() < need
+                or self._scratch[0].device != x.device):
+            self._scratch = [torch.empty((need,), dtype=torch.float32, device=x.device) for _ in range(n_scratch)]
+        x_lo = None
+        for l, (k, scale, shift, w_cat) in enumerate(self._device_weights()):
             last = l == self.n_layers - 1
             shape = (n, h - 2, w - 2, self.filters)
+            numel = n * (h - 2) * (w - 2) * self.filters
             if last:
                 y = torch.empty(shape, dtype=torch.float32, device=x.device)
+                y_lo = None
+            elif self.tensor_cores:
+                y = self._scratch[2 * (l & 1)][:numel].view(shape)
+                y_lo = self._scratch[2 * (l & 1) + 1][:numel].view(shape)
             else:
-                y = self._scratch[l & 1][:n * (h - 2) * (w - 2) * self.filters].view(shape)
-            _lib.call("rn_conv3x3_bn_relu", x.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
-                      n, h, w, cin, 0 if last else 1, current_stream_ptr())
+                y = self._scratch[l & 1][:numel].view(shape)
+                y_lo = None
+            if self.tensor_cores and x_lo is not None:
+                _lib.call("rn_conv3x3_bn_relu_tc", x.data_ptr(), x_lo.data_ptr(), w_cat.data_ptr(), scale.data_ptr(),
+                          shift.data_ptr(), y.data_ptr(), y_lo.data_ptr() if y_lo is not None else None, n, h, w,
+                          0 if last else 1, st)
+            elif y_lo is not None:
+                _lib.call("rn_conv3x3_bn_relu_split", x.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                          y.data_ptr(), y_lo.data_ptr(), n, h, w, cin, 0 if last else 1, st)
+            else:
+                _lib.call("rn_conv3x3_bn_relu", x.data_ptr(), k.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
+                          n, h, w, cin, 0 if last else 1, st)
             self.launches += 1
-            x, h, w, cin = y, h - 2, w - 2, self.filters
+            x, x_lo, h, w, cin = y, y_lo, h - 2, w - 2, self.filters
         return x
 
     def predict(self, X, batch_size=None):

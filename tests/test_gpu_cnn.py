@@ -13,19 +13,25 @@ def torch_cuda():
     return torch
 
 
-@pytest.mark.parametrize("channels,shape", [(3, (2, 37, 45)), (1, (1, 30, 75)), (3, (3, 11, 11)), (3, (1, 64, 97))])
-def test_simple_cnn_vs_oracle(torch_cuda, channels, shape):
+@pytest.mark.parametrize("tensor_cores", [False, True])
+@pytest.mark.parametrize("channels,shape", [(3, (2, 37, 45)), (1, (1, 30, 75)), (3, (3, 11, 11)), (3, (1, 64, 97)),
+                                            (3, (2, 150, 300))])
+def test_simple_cnn_vs_oracle(torch_cuda, channels, shape, tensor_cores, parity_log):
+    """Both code paths of the 32 -> 32 layers: fp32 on the CUDA cores and 3 x TF32 on tcgen05 (rn_cnn_tc.cuh; the
+    last shape spans several 128-pixel strips with a partial one and several 32-row chunks with a partial one)."""
     from oracle import cnn_np
     from raynet_b200.models import SimpleCNN
     rng = np.random.default_rng(3)
-    model = SimpleCNN.random_init(channels=channels, seed=5)
+    model = SimpleCNN.random_init(channels=channels, seed=5, tensor_cores=tensor_cores)
     X = rng.uniform(0, 1, size=shape + (channels,)).astype(np.float32)
     got = model.predict(X)
     ref = cnn_np.simple_cnn_forward(X, model.get_weights())
     assert got.shape == ref.shape == (shape[0], shape[1] - 10, shape[2] - 10, 32)
     scale = np.abs(ref).max()
     err = np.abs(got - ref).max()
-    print("cnn %s: max |features - oracle| = %.2e (max |feature| %.2f)" % (shape, err, scale))
+    print("cnn %s tensor_cores=%s: max |features - oracle| = %.2e (max |feature| %.2f)" % (shape, tensor_cores, err, scale))
+    parity_log["cnn/%s/%s" % ("tcgen05_3xtf32" if tensor_cores else "cuda_cores_fp32", "x".join(map(str, shape)))] = {
+        "max_abs_err_vs_float64_oracle": float(err), "max_abs_feature": float(scale)}
     assert err <= 1e-5 * max(scale, 1.0)
     assert model.launches == 5
 

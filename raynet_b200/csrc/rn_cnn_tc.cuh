@@ -33,6 +33,9 @@
 #define RN_TC_ROWS 136                    // shared-memory rows per stage half (130 used: 128 + 2 halo pixels), 1024-byte multiple
 #define RN_TC_STAGES 4
 #define RN_TC_CHUNK_ROWS 32               // output rows per work unit
+#ifndef RN_TC_NOINC
+#define RN_TC_NOINC 0                     // 1: the stage's mbarrier tracks the copies itself (cp.async.mbarrier.arrive.noinc)
+#endif
 #define RN_TC_HALF_BYTES (RN_TC_ROWS * 128)          // 17408 = 17 * 1024
 #define RN_TC_STAGE_BYTES (2 * RN_TC_HALF_BYTES)     // hi + lo
 #define RN_TC_B_BYTES (9 * 64 * 128)                 // per tap [B_hi ; B_lo]: 64 rows of 128 bytes
@@ -137,6 +140,9 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(ConvTcArgs a) {
 
     if (warp == 0) {
         // ================= producer =================
+        // Every lane lets the mbarrier of the stage track its own copies (cp.async.mbarrier.arrive.noinc: the arrival
+        // happens when the lane's cp.async operations issued so far have landed), so the warp never waits for data
+        // and goes straight on to the next free stage.
         int ri = 0, prev_stage = -1;
         TcUnit t;
         for (int64_t u = blockIdx.x; rn_tc_unit(a, u, t); u += gridDim.x) {
@@ -153,6 +159,10 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(ConvTcArgs a) {
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rn_tc_smem(dst_hi + off)), "l"(a.in_hi + row_off + i * 4) : "memory");
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rn_tc_smem(dst_lo + off)), "l"(a.in_lo + row_off + i * 4) : "memory");
                 }
+#if RN_TC_NOINC
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(rn_tc_smem(&full[stage])) : "memory");
+                (void)prev_stage;
+#else
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 if (prev_stage >= 0) {      // the row before this one has landed: hand it to the MMA warp
                     asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -160,13 +170,18 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(ConvTcArgs a) {
                     rn_tc_mbar_arrive(&full[prev_stage]);
                 }
                 prev_stage = stage;
+#endif
             }
         }
+#if RN_TC_NOINC
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#else
         if (prev_stage >= 0) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             rn_tc_mbar_arrive(&full[prev_stage]);
         }
+#endif
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {

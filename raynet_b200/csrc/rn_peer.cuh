@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(512) peer_allreduce_kernel(PeerArgs a) {
         float4 *dst[WORLD ? WORLD : 1];
 #pragma unroll
         for (int p = 0; p < WORLD; p++) {   // peers staggered by rank so that the links are loaded evenly
-            const int q = (a.rank + p) % WORLD;
+            const int q = (a.rank + p) % (WORLD ? WORLD : 1);
             src[p] = reinterpret_cast<const float4 *>(a.partial[q]);
             dst[p] = reinterpret_cast<float4 *>(a.result[q]);
         }

@@ -1147,10 +1147,38 @@ int rn_conv3x3_bn_relu_tc(const float *in_hi, const float *in_lo, const float *w
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return fail(RN_ERR_CUDA, "conv3x3_tc setup: %s", cudaGetErrorString(e));
+    // TMA descriptors of the two activation arrays viewed as [pixels][32 channels]: box = 130 pixels x 32 channels,
+    // 128-byte swizzle.  cuTensorMapEncodeTiled comes from the driver through the runtime (no libcuda link).
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !fn) return fail(RN_ERR_CUDA, "cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t pixels = (cuuint64_t)n_images * height * width;
+    if (pixels >= (1ull << 31)) return fail(RN_ERR_UNSUPPORTED, "conv3x3_tc: more than 2^31 pixels per call");
+    const cuuint64_t gdim[2] = {32, pixels};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {32, RN_TC_PX + 2};
+    const cuuint32_t estride[2] = {1, 1};
+    CUtensorMap tm_hi, tm_lo;
+    CUresult cr = encode(&tm_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(in_hi), gdim, gstride, box, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr == CUDA_SUCCESS)
+        cr = encode(&tm_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(in_lo), gdim, gstride, box, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(RN_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)cr);
     ConvTcArgs a = {in_hi, in_lo, w_cat, scale, shift, out_hi, out_lo, n_images, height, width, relu};
     const int ho = height - 2, wo = width - 2;
     const int64_t units = (int64_t)n_images * ((wo + RN_TC_PX - 1) / RN_TC_PX) * ((ho + RN_TC_CHUNK_ROWS - 1) / RN_TC_CHUNK_ROWS);
-    conv3x3_tc_kernel<<<(unsigned)(units < sms ? units : sms), 192, RN_TC_SMEM_BYTES, S(stream)>>>(a);
+    conv3x3_tc_kernel<<<(unsigned)(units < sms ? units : sms), 192, RN_TC_SMEM_BYTES, S(stream)>>>(tm_hi, tm_lo, a);
     return check_launch("conv3x3_tc_kernel");
 }
 

@@ -20,12 +20,16 @@
 // operand traffic of three separate products.  The epilogue adds the two column halves.
 //
 // Warp roles (192 threads, one CTA per SM, persistent over (image, 128-pixel strip, 32-row chunk) units):
-//   warp 0      producer: 16-byte cp.async of the next input row (hi and lo) into the ring, swizzled
+//   warp 0      producer: one lane issues two TMA tensor copies (cp.async.bulk.tensor.2d, 128B swizzle) per input row
+//               (hi and lo) into the ring.  (A first version copied with per-lane 16-byte cp.async: its 130 issue
+//               slots per row sat on the critical path between the completion of one row's MMAs and the next.)
 //   warp 1      one elected lane issues the MMAs; tcgen05.commit releases ring stages / publishes accumulators
 //   warps 2-5   epilogue: tcgen05.ld (each warp its 32-lane quarter), folded batch norm (+ ReLU), hi / lo split,
 //               128-byte rows to HBM; two accumulator stages in TMEM so the epilogue overlaps the next row's MMAs
 // mbarriers: full[4] (producer -> MMA), empty[4] (MMA -> producer, by tcgen05.commit), acc_full[2], acc_empty[2].
 #pragma once
+
+#include <cuda.h>      // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint, no libcuda link)
 
 #include "rn_common.cuh"
 
@@ -33,9 +37,6 @@
 #define RN_TC_ROWS 136                    // shared-memory rows per stage half (130 used: 128 + 2 halo pixels), 1024-byte multiple
 #define RN_TC_STAGES 4
 #define RN_TC_CHUNK_ROWS 32               // output rows per work unit
-#ifndef RN_TC_NOINC
-#define RN_TC_NOINC 0                     // 1: the stage's mbarrier tracks the copies itself (cp.async.mbarrier.arrive.noinc)
-#endif
 #define RN_TC_HALF_BYTES (RN_TC_ROWS * 128)          // 17408 = 17 * 1024
 #define RN_TC_STAGE_BYTES (2 * RN_TC_HALF_BYTES)     // hi + lo
 #define RN_TC_B_BYTES (9 * 64 * 128)                 // per tap [B_hi ; B_lo]: 64 rows of 128 bytes
@@ -106,7 +107,8 @@ __device__ __forceinline__ bool rn_tc_unit(const ConvTcArgs &a, int64_t u, TcUni
     return true;
 }
 
-__global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(ConvTcArgs a) {
+__global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
+                                                            const __grid_constant__ CUtensorMap tm_lo, ConvTcArgs a) {
     extern __shared__ unsigned char rn_tc_smem_raw[];
     __shared__ __align__(8) uint64_t full[RN_TC_STAGES], empty[RN_TC_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(ConvTcArgs a) {
     }
     if (tid < 32) { sScale[tid] = __ldg(a.scale + tid); sShift[tid] = __ldg(a.shift + tid); }
     if (tid == 0) {
-        for (int s = 0; s < RN_TC_STAGES; s++) { rn_tc_mbar_init(&full[s], 32); rn_tc_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < RN_TC_STAGES; s++) { rn_tc_mbar_init(&full[s], 1); rn_tc_mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; s++) { rn_tc_mbar_init(&acc_full[s], 1); rn_tc_mbar_init(&acc_empty[s], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -140,80 +142,73 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(ConvTcArgs a) {
 
     if (warp == 0) {
         // ================= producer =================
-        // Every lane lets the mbarrier of the stage track its own copies (cp.async.mbarrier.arrive.noinc: the arrival
-        // happens when the lane's cp.async operations issued so far have landed), so the warp never waits for data
-        // and goes straight on to the next free stage.
-        int ri = 0, prev_stage = -1;
-        TcUnit t;
-        for (int64_t u = blockIdx.x; rn_tc_unit(a, u, t); u += gridDim.x) {
-            const int64_t img_off = (int64_t)t.img * a.hi * a.wi;
-            for (int r = 0; r < t.rows + 2; r++, ri++) {
-                const int stage = ri % RN_TC_STAGES;
-                rn_tc_mbar_wait(&empty[stage], ((ri / RN_TC_STAGES) & 1) ^ 1);
-                unsigned char *dst_hi = base + stage * RN_TC_STAGE_BYTES, *dst_lo = dst_hi + RN_TC_HALF_BYTES;
-                const int64_t row_off = (img_off + (int64_t)(t.oy0 + r) * a.wi + t.x0) * 32;
-                const int npx = min(RN_TC_PX + 2, a.wi - t.x0);      // pixels of this row inside the image
-                for (int i = lane; i < npx * 8; i += 32) {
-                    const int p = i >> 3, c = i & 7;
-                    const uint32_t off = (uint32_t)(p * 128 + ((c ^ (p & 7)) << 4));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rn_tc_smem(dst_hi + off)), "l"(a.in_hi + row_off + i * 4) : "memory");
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rn_tc_smem(dst_lo + off)), "l"(a.in_lo + row_off + i * 4) : "memory");
-                }
-#if RN_TC_NOINC
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(rn_tc_smem(&full[stage])) : "memory");
-                (void)prev_stage;
-#else
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                if (prev_stage >= 0) {      // the row before this one has landed: hand it to the MMA warp
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    rn_tc_mbar_arrive(&full[prev_stage]);
-                }
-                prev_stage = stage;
-#endif
-            }
-        }
-#if RN_TC_NOINC
-        asm volatile("cp.async.wait_all;" ::: "memory");
-#else
-        if (prev_stage >= 0) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            rn_tc_mbar_arrive(&full[prev_stage]);
-        }
-#endif
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+        // One lane, two TMA tensor copies per input row (hi and lo): a box of 130 pixels x 32 channels of the
+        // [pixels][32] view of the activations lands as 130 swizzled 128-byte rows (CU_TENSOR_MAP_SWIZZLE_128B writes
+        // exactly the layout the MMA descriptors read); completion is counted in bytes on the stage's mbarrier.  Boxes
+        // that run past the end of an image row read the next row's pixels (never used), past the end of the tensor zeros.
         if (lane == 0) {
-            constexpr uint32_t idesc64 = rn_tc_idesc(RN_TC_PX, 64), idesc32 = rn_tc_idesc(RN_TC_PX, 32);
-            const uint32_t sB_addr = rn_tc_smem(sB);
-            int ri_base = 0, tile = 0;
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
+            int ri = 0;
             TcUnit t;
             for (int64_t u = blockIdx.x; rn_tc_unit(a, u, t); u += gridDim.x) {
-                for (int j = 0; j < t.rows; j++, tile++) {
-                    const int as = tile & 1;
-                    rn_tc_mbar_wait(&acc_empty[as], ((tile >> 1) & 1) ^ 1);
+                const int pix0 = (t.img * a.hi + t.oy0) * a.wi + t.x0;
+                for (int r = 0; r < t.rows + 2; r++, ri++) {
+                    const int stage = ri % RN_TC_STAGES;
+                    rn_tc_mbar_wait(&empty[stage], ((ri / RN_TC_STAGES) & 1) ^ 1);
+                    const uint32_t dst_hi = rn_tc_smem(base + stage * RN_TC_STAGE_BYTES), dst_lo = dst_hi + RN_TC_HALF_BYTES;
+                    const uint32_t bar = rn_tc_smem(&full[stage]);
+                    const int pix = pix0 + r * a.wi;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * (RN_TC_PX + 2) * 128) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(dst_hi), "l"(&tm_hi), "r"(0), "r"(pix), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(dst_lo), "l"(&tm_lo), "r"(0), "r"(pix), "r"(bar) : "memory");
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        // The whole warp runs the loop (warp-uniform control flow and addresses: the descriptors stay in uniform
+        // registers); only the tcgen05 instructions themselves are issued by one lane.
+        const bool leader = lane == 0;
+        constexpr uint32_t idesc64 = rn_tc_idesc(RN_TC_PX, 64), idesc32 = rn_tc_idesc(RN_TC_PX, 32);
+        const uint64_t desc_b0 = rn_tc_desc(rn_tc_smem(sB));
+        const uint64_t desc_a0 = rn_tc_desc(rn_tc_smem(base));
+        int ri_base = 0, tile = 0;
+        TcUnit t;
+        for (int64_t u = blockIdx.x; rn_tc_unit(a, u, t); u += gridDim.x) {
+            for (int j = 0; j < t.rows; j++, tile++) {
+                const int as = tile & 1;
+                rn_tc_mbar_wait(&acc_empty[as], ((tile >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem + (uint32_t)(as * 64);
+                uint32_t accumulate = 0;
+                for (int ky = 0; ky < 3; ky++) {
+                    const int row = ri_base + j + ky, stage = row % RN_TC_STAGES;
+                    rn_tc_mbar_wait(&full[stage], (row / RN_TC_STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t d_tmem = tmem + (uint32_t)(as * 64);
-                    uint32_t accumulate = 0;
-                    for (int ky = 0; ky < 3; ky++) {
-                        const int row = ri_base + j + ky, stage = row % RN_TC_STAGES;
-                        rn_tc_mbar_wait(&full[stage], (row / RN_TC_STAGES) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_hi = rn_tc_smem(base + stage * RN_TC_STAGE_BYTES), a_lo = a_hi + RN_TC_HALF_BYTES;
+                    // descriptors differ in their 14-bit start-address field only (units of 16 bytes)
+                    const uint64_t da_hi = desc_a0 + (uint64_t)((stage * RN_TC_STAGE_BYTES) >> 4);
+                    const uint64_t da_lo = da_hi + (uint64_t)(RN_TC_HALF_BYTES >> 4);
+                    const uint64_t db_ky = desc_b0 + (uint64_t)((ky * 3 * 64 * 128) >> 4);
+                    if (leader) {
 #pragma unroll
                         for (int kx = 0; kx < 3; kx++) {
-                            const uint32_t b_tap = sB_addr + (uint32_t)((ky * 3 + kx) * 64 * 128);
 #pragma unroll
                             for (int k = 0; k < 4; k++) {
-                                const uint32_t sh = (uint32_t)(kx * 128 + k * 32);
-                                const uint64_t db = rn_tc_desc(b_tap + k * 32);
-                                rn_tc_mma(d_tmem, rn_tc_desc(a_hi + sh), db, idesc64, accumulate);   // hi hi | hi lo
-                                rn_tc_mma(d_tmem, rn_tc_desc(a_lo + sh), db, idesc32, 1);            // + lo hi into columns 0..31
+                                const uint64_t sh = (uint64_t)((kx * 128 + k * 32) >> 4);
+                                const uint64_t db = db_ky + (uint64_t)((kx * 64 * 128 + k * 32) >> 4);
+                                rn_tc_mma(d_tmem, da_hi + sh, db, idesc64, accumulate);   // hi hi | hi lo
+                                rn_tc_mma(d_tmem, da_lo + sh, db, idesc32, 1);            // + lo hi into columns 0..31
                                 accumulate = 1;
                             }
                         }
                     }
+                    __syncwarp();
+                }
+                if (leader) {
                     rn_tc_commit(&acc_full[as]);                                  // accumulators of this row are complete
                     rn_tc_commit(&empty[(ri_base + j) % RN_TC_STAGES]);          // input row j is not needed any more
                     if (j == t.rows - 1) {
@@ -221,10 +216,10 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(ConvTcArgs a) {
                         rn_tc_commit(&empty[(ri_base + j + 2) % RN_TC_STAGES]);
                     }
                 }
-                ri_base += t.rows + 2;
+                __syncwarp();
             }
+            ri_base += t.rows + 2;
         }
-        __syncwarp();
     } else {
         // ================= epilogue =================
         const int q = warp & 3;                 // this warp's TMEM lane quarter

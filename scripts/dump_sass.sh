@@ -23,4 +23,4 @@ dump depth3 _Z13depth3_kernel5RnDev10Depth2Args
 dump peer_allreduce _Z21peer_allreduce_kernel8PeerArgs
 dump bp_parity _Z16bp_parity_kernelILb0EEv5RnDev10ParityArgs
 dump bp4_first_mapped_nch4 _Z23bp4_first_mapped_kernelILi4EEv5RnDev9FirstArgs
-dump conv3x3_tc _Z17conv3x3_tc_kernel10ConvTcArgs
+dump conv3x3_tc _Z17conv3x3_tc_kernel14CUtensorMap_stS_10ConvTcArgs

@@ -81,6 +81,13 @@ __device__ __forceinline__ void rn_tc_mma(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void rn_tc_commit(uint64_t *bar) {   // arrives on bar when every MMA issued so far has completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(rn_tc_smem(bar)) : "memory");
 }
+// one lane of a converged warp (elect.sync: the form ptxas keeps warp-uniform, so that descriptors computed from
+// warp-uniform values stay in uniform registers instead of being moved there lane by lane)
+__device__ __forceinline__ bool rn_tc_elect() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void rn_tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -172,7 +179,6 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constan
         // ================= MMA issuer =================
         // The whole warp runs the loop (warp-uniform control flow and addresses: the descriptors stay in uniform
         // registers); only the tcgen05 instructions themselves are issued by one lane.
-        const bool leader = lane == 0;
         constexpr uint32_t idesc64 = rn_tc_idesc(RN_TC_PX, 64), idesc32 = rn_tc_idesc(RN_TC_PX, 32);
         const uint64_t desc_b0 = rn_tc_desc(rn_tc_smem(sB));
         const uint64_t desc_a0 = rn_tc_desc(rn_tc_smem(base));
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constan
                     const uint64_t da_hi = desc_a0 + (uint64_t)((stage * RN_TC_STAGE_BYTES) >> 4);
                     const uint64_t da_lo = da_hi + (uint64_t)(RN_TC_HALF_BYTES >> 4);
                     const uint64_t db_ky = desc_b0 + (uint64_t)((ky * 3 * 64 * 128) >> 4);
-                    if (leader) {
+                    if (rn_tc_elect()) {
 #pragma unroll
                         for (int kx = 0; kx < 3; kx++) {
 #pragma unroll
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constan
                     }
                     __syncwarp();
                 }
-                if (leader) {
+                if (rn_tc_elect()) {
                     rn_tc_commit(&acc_full[as]);                                  // accumulators of this row are complete
                     rn_tc_commit(&empty[(ri_base + j) % RN_TC_STAGES]);          // input row j is not needed any more
                     if (j == t.rows - 1) {

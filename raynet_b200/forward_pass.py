@@ -14,6 +14,8 @@ SURVEY.md 2.2 "latent defects" #3 for why the literal host loop of forward_pass.
 is not reproduced): features and the whole front end once per image, `bp_iterations`
 synchronous sweeps over all rays of all images, then one depth pass per image.
 """
+import time
+
 import numpy as np
 import torch
 
@@ -232,6 +234,8 @@ class RayNetForwardPass(ForwardPass):
         self._feat_dev = None
         self._copy_stream = None
         self._staging = {}
+        self.profile = False                    # True: forward_pass() fills self.timings (ms per stage, synchronised)
+        self.timings = {}
         self.h2d_bytes = 0                      # bytes copied host->device / device->host by the last
         self.d2h_bytes = 0                      # forward_pass() call (bench.py's e2e accounting)
 
@@ -328,6 +332,13 @@ class RayNetForwardPass(ForwardPass):
         rank = dist.get_rank() if world > 1 else 0
         by_rays = world > 1 and self.shard == "rays"
         img_ids = list(range(start_img_idx, end_img_idx, skip))
+        stamps = []
+
+        def stamp(name):        # self.profile = True: host wall clock per stage, the device drained at every stamp
+            if self.profile:
+                torch.cuda.synchronize(dev)
+                stamps.append((name, time.perf_counter()))
+        stamp("start")
         rays = [self.get_valid_rays_per_image(scene, i) for i in img_ids]
         self.h2d_bytes = self.d2h_bytes = 0
         # ---- this rank's segments: (position in img_ids, first ray, last ray) -------------------
@@ -425,6 +436,7 @@ class RayNetForwardPass(ForwardPass):
                         copied[k] = torch.cuda.Event()
                         copied[k].record()
                 self.h2d_bytes += f_host.numel() * 4
+        stamp("features")
         F = int(self._feat_dev.shape[-1])
         if self.engine is None or self.engine.capacity < total_cap or self.engine.max_segment_rays < min(max_seg, total_cap):
             self.engine = None                     # release the old state before the larger one is allocated
@@ -473,8 +485,10 @@ class RayNetForwardPass(ForwardPass):
                 if slot[v] in copied:
                     main.wait_event(copied.pop(slot[v]))
             self.engine.score_image(j, self._feat_dev, P_dev, view_ids=view_ids, n_feature_slots=n_slots)
+        stamp("frontend")
         # ---- BP sweeps + depth -----------------------------------------------------------------
         self.engine.run_bp(self.bp_iterations)
+        stamp("bp")
         if by_rays:
             # every rank yields complete maps: this rank's block goes into a zeroed job-sized buffer, one SUM
             # all-reduce (x + 0 is exact) completes it everywhere
@@ -496,8 +510,12 @@ class RayNetForwardPass(ForwardPass):
         depth_host = self._pinned("depth", (int(depth_dev.shape[0]),), torch.float32)
         depth_host.copy_(depth_dev, non_blocking=True)       # pinned destination: one DMA, no staging copy
         torch.cuda.current_stream(dev).synchronize()
+        stamp("depth")
         depth = depth_host.numpy().copy()
         self.d2h_bytes += depth.nbytes
+        stamp("copy_out")
+        if self.profile:
+            self.timings = dict((b[0], (b[1] - a[1]) * 1e3) for a, b in zip(stamps[:-1], stamps[1:]))
         for k, ref_idx in enumerate(img_ids):
             start, n = seg_of[k]
             if len(rays[k]) == H * W:

@@ -234,6 +234,7 @@ class RayNetForwardPass(ForwardPass):
         self._feat_dev = None
         self._copy_stream = None
         self._staging = {}
+        self._copy_pool = None
         self.profile = False                    # True: forward_pass() fills self.timings (ms per stage, synchronised)
         self.timings = {}
         self.h2d_bytes = 0                      # bytes copied host->device / device->host by the last
@@ -511,7 +512,18 @@ class RayNetForwardPass(ForwardPass):
         depth_host.copy_(depth_dev, non_blocking=True)       # pinned destination: one DMA, no staging copy
         torch.cuda.current_stream(dev).synchronize()
         stamp("depth")
-        depth = depth_host.numpy().copy()
+        # the pinned buffer is reused by the next call: hand out a private copy (four threads: a single memcpy of the
+        # job's depth maps is the largest host-side item of a call on a multi-GPU box)
+        src = depth_host.numpy()
+        depth = np.empty_like(src)
+        if src.shape[0] >= (1 << 20):
+            if self._copy_pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._copy_pool = ThreadPoolExecutor(4)
+            cuts = [src.shape[0] * i // 4 for i in range(5)]
+            list(self._copy_pool.map(lambda ab: np.copyto(depth[ab[0]:ab[1]], src[ab[0]:ab[1]]), zip(cuts[:-1], cuts[1:])))
+        else:
+            np.copyto(depth, src)
         self.d2h_bytes += depth.nbytes
         stamp("copy_out")
         if self.profile:

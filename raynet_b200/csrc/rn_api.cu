@@ -173,32 +173,43 @@ int launch_simmap(const RnDev &d, SimMapArgs a, bool mapping, cudaStream_t st) {
 
 // Resident front end, F = 32 (rn_simmap3.cuh): similarity + softmax -> S_planes scratch (caller-owned,
 // n_rays x depth_planes floats), then plane->voxel mapping -> s_hat, lin.
-inline size_t simscore3_smem(const RnDev &d) {
-    return sizeof(float) * (rn_simscore3_cta_words(d.V) + 4 * rn_simscore3_warp_words(d.D, d.V));
+inline size_t simscore3_smem(const RnDev &d, int warps = 4) {
+    return sizeof(float) * (rn_simscore3_cta_words(d.V) + (size_t)warps * rn_simscore3_warp_words(d.D, d.V));
 }
 
-template <int VT>
-int launch_simscore3(const RnDev &d, const SimMapArgs &a, size_t smem, cudaStream_t st) {
+template <int VT, int kW>
+int launch_simscore3_w(const RnDev &d, const SimMapArgs &a, cudaStream_t st) {
+    const size_t smem = simscore3_smem(d, kW);
     static SmemOptIn opt;
-    if (int rc = opt.ensure(simscore3_kernel<VT>, smem, "simscore3_kernel")) return rc;
-    simscore3_kernel<VT><<<(unsigned)((a.n_rays + 3) / 4), 128, smem, st>>>(d, a);
+    if (int rc = opt.ensure(simscore3_kernel<VT, kW>, smem, "simscore3_kernel")) return rc;
+    simscore3_kernel<VT, kW><<<(unsigned)((a.n_rays + kW - 1) / kW), 32 * kW, smem, st>>>(d, a);
     return check_launch("simscore3_kernel");
+}
+
+// The wide flavour (a compact patch of RN_SIMSCORE_WIDE rays per CTA: their plane samples share pixels of the other
+// views, which then hit in L1) is used where two such CTAs fit on an SM, i.e. the SM keeps its 32 warps.
+template <int VT>
+int launch_simscore3(const RnDev &d, const SimMapArgs &a, cudaStream_t st) {
+#if RN_SIMSCORE_WIDE > 0
+    if (a.tile_len > 0 && (32 / RN_SIMSCORE_WIDE) * (simscore3_smem(d, RN_SIMSCORE_WIDE) + 1024) <= 200 * 1024)
+        return launch_simscore3_w<VT, RN_SIMSCORE_WIDE>(d, a, st);
+#endif
+    return launch_simscore3_w<VT, 4>(d, a, st);
 }
 
 int launch_plane_scores(const RnDev &d, SimMapArgs a, cudaStream_t st) {
     if (a.n_rays <= 0) return RN_OK;
     a.tile_len = tile_len_for(d, a.n_rays);
     a.tile_mode = 2;
-    const size_t smem_a = simscore3_smem(d);
     switch (d.V) {   // common view counts get fully unrolled loops
-        case 3: return launch_simscore3<3>(d, a, smem_a, st);
-        case 5: return launch_simscore3<5>(d, a, smem_a, st);
-        case 7: return launch_simscore3<7>(d, a, smem_a, st);
-        case 9: return launch_simscore3<9>(d, a, smem_a, st);
-        case 11: return launch_simscore3<11>(d, a, smem_a, st);
-        case 15: return launch_simscore3<15>(d, a, smem_a, st);
+        case 3: return launch_simscore3<3>(d, a, st);
+        case 5: return launch_simscore3<5>(d, a, st);
+        case 7: return launch_simscore3<7>(d, a, st);
+        case 9: return launch_simscore3<9>(d, a, st);
+        case 11: return launch_simscore3<11>(d, a, st);
+        case 15: return launch_simscore3<15>(d, a, st);
     }
-    return launch_simscore3<0>(d, a, smem_a, st);
+    return launch_simscore3<0>(d, a, st);
 }
 
 int launch_planemap3(const RnDev &d, SimMapArgs a, cudaStream_t st) {

@@ -83,7 +83,13 @@ template <int N>
 __device__ __forceinline__ void rn_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // warps per CTA of a length class: the double-buffered rows of one warp take 24 * NCH * 128 bytes
-__host__ __device__ constexpr int rn_bp4_warps(int nch) { return nch <= 6 ? 4 : 2; }
+#ifndef RN_BP4_W4_MAX
+#define RN_BP4_W4_MAX 6       // length classes up to this many chunks use CTAs of 4 warps, longer ones of 2
+#endif
+#ifndef RN_BP4_W8_MAX
+#define RN_BP4_W8_MAX 0       // ... and up to this many chunks CTAs of 8 warps
+#endif
+__host__ __device__ constexpr int rn_bp4_warps(int nch) { return nch <= RN_BP4_W8_MAX ? 8 : (nch <= RN_BP4_W4_MAX ? 4 : 2); }
 // shared memory words of one warp: 2 x (lin, s_hat) [+ 2 x msgs unless first sweep] rows of NCH * 128 words.
 // The transposition scratch of chunk c is the 128 words of the CURRENT ray's s_hat chunk c, dead once its
 // four values per lane have been read.

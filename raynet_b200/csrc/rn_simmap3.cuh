@@ -25,8 +25,11 @@
 
 #include "rn_kernels.cuh"
 
-#ifndef RN_SIMSCORE_MINB
-#define RN_SIMSCORE_MINB 8
+#ifndef RN_SIMSCORE_WIDE
+#define RN_SIMSCORE_WIDE 16      // warps (rays) of the wide CTA flavour: 16 (4x4 pixel patch) or 32 (8x4); 0 = never
+#endif
+#ifndef RN_SIMSCORE_SYNC
+#define RN_SIMSCORE_SYNC 0       // > 0: the CTA's warps re-align every this many plane groups (bar.sync)
 #endif
 #ifndef RN_SIMSCORE_UNROLL
 #define RN_SIMSCORE_UNROLL 2     // plane groups (of 4 planes x V gathers) in flight per warp
@@ -93,6 +96,7 @@ __device__ __forceinline__ void rn_plane_scores(const RnDev &p, const SimMapArgs
     constexpr int kUnroll = RN_SIMSCORE_UNROLL;
 #pragma unroll kUnroll
     for (int k0 = 0; k0 < D; k0 += 4) {
+        if (RN_SIMSCORE_SYNC > 0 && (k0 % (4 * RN_SIMSCORE_SYNC)) == 0) __syncthreads();
         const int k = min(k0 + g, D - 1);
         uint64_t s01 = r01, s23 = r23, q01 = rq01, q23 = rq23;
         if constexpr (VT > 0) {
@@ -137,8 +141,30 @@ __device__ __forceinline__ void rn_plane_scores(const RnDev &p, const SimMapArgs
 // a2: plane-sweep similarity + softmax -> S_planes [n][D].  All warps of all CTAs spend their time
 // in the projection / gather loops (nothing else competes for registers and shared memory), which
 // is what keeps enough 128-byte feature gathers in flight to load the L2.
-template <int VT>
-__global__ void __launch_bounds__(128, RN_SIMSCORE_MINB) simscore3_kernel(RnDev p, SimMapArgs a) {
+// Which ray of its 64-pixel tile warp `wid` of CTA `cta` serves.  With 4 warps a CTA takes 4 vertical neighbours;
+// with 16 / 32 warps a compact 4x4 / 8x4 patch (x, y), so that the rays whose plane samples fall on the same pixels
+// of the other views are resident on ONE SM at the same time and meet in its L1 (scratch/sim_l1b.py: modelled L1
+// hit rate 0.15 -> 0.39 / 0.46 on the C3 rig).
+template <int kW>
+__device__ __forceinline__ int64_t rn_simscore_slot(int64_t cta, int wid, int64_t tile_len) {
+    const int64_t t = cta * kW + wid;
+    if (tile_len <= 0 || kW == 4) return t;
+    const int in = (int)(t & 63);
+    int xo, yo;
+    if (kW == 16) {
+        const int q = in >> 4, w = in & 15;
+        xo = (q >> 1) * 4 + (w >> 2);
+        yo = (q & 1) * 4 + (w & 3);
+    } else {
+        const int h = in >> 5, w = in & 31;
+        xo = w >> 2;
+        yo = h * 4 + (w & 3);
+    }
+    return (t & ~(int64_t)63) | (xo << 3) | yo;
+}
+
+template <int VT, int kW>
+__global__ void __launch_bounds__(32 * kW, 32 / kW) simscore3_kernel(RnDev p, SimMapArgs a) {   // 32 warps per SM at <= 64 registers
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = p.D, V = VT ? VT : p.V;   // VT > 0: compile-time view count, loops fully unrolled
@@ -158,9 +184,10 @@ __global__ void __launch_bounds__(128, RN_SIMSCORE_MINB) simscore3_kernel(RnDev 
     const float fDm1 = (float)(D - 1);
     const int fshift = p.shift;
 
-    const int64_t t = (int64_t)blockIdx.x * 4 + wid;
-    if (t >= a.n_rays) return;
-    const int64_t r = rn_tiled_position(t, a.tile_len, p.H, a.tile_mode & 0xff);
+    const int64_t t = rn_simscore_slot<kW>(blockIdx.x, wid, a.tile_len);
+    if (!RN_SIMSCORE_SYNC && t >= a.n_rays) return;
+    const bool live = t < a.n_rays;
+    const int64_t r = live ? rn_tiled_position(t, a.tile_len, p.H, a.tile_mode & 0xff) : 0;
     float rs[3], re[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -208,7 +235,7 @@ __global__ void __launch_bounds__(128, RN_SIMSCORE_MINB) simscore3_kernel(RnDev 
                 }
                 const int off = (int)((uint32_t)rn_feature_offset(p, vbase, fx, fy) * 4u);   // BYTE offset (feature volume < 4 GiB)
                 if (kk[h] < D) {
-                    sOff[kk[h] * VP + v] = off;
+                    sOff[kk[h] * VP + v] = off;   // (16-byte stores of a plane's offsets, conflict-free, measured slower: 12.55 vs 11.94 ms)
                     if (v == 0) {
                         if (kk[h] == lane) ref_off = off;
                         else if (off != ref_off) ref_same = false;
@@ -240,7 +267,8 @@ __global__ void __launch_bounds__(128, RN_SIMSCORE_MINB) simscore3_kernel(RnDev 
         ssum += ev;
     }
     ssum = rn_warp_sum(ssum);
-    for (int k = lane; k < D; k += 32) a.S_planes[r * (int64_t)D + k] = sS[k] / ssum;
+    if (live)
+        for (int k = lane; k < D; k += 32) a.S_planes[r * (int64_t)D + k] = sS[k] / ssum;
 }
 
 // a4: plane -> voxel mapping (planes_voxels_mapping.cu:6-92) + clip_and_renorm (mrf_np.py:4-8) from

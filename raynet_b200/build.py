@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "rn_api.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", h) for h in ("rn_kernels.cuh", "rn_engine.cuh", "rn_bp4.cuh", "rn_parity.cuh", "rn_backward.cuh", "rn_peer.cuh", "rn_first.cuh", "rn_cnn_tc.cuh", "rn_simmap3.cuh", "rn_cnn.cuh", "rn_fusion.cuh", "rn_common.cuh")] + [
+DEPS = [SRC] + [os.path.join(HERE, "csrc", h) for h in ("rn_kernels.cuh", "rn_engine.cuh", "rn_bp4.cuh", "rn_bp4c.cuh", "rn_parity.cuh", "rn_backward.cuh", "rn_peer.cuh", "rn_first.cuh", "rn_cnn_tc.cuh", "rn_simmap3.cuh", "rn_cnn.cuh", "rn_fusion.cuh", "rn_common.cuh")] + [
     os.path.join(ROOT, "include", "raynet_b200.h")]
 LIB = os.path.join(HERE, "libraynet_b200.so")
 

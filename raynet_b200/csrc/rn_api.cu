@@ -7,6 +7,12 @@
 
 #include "rn_kernels.cuh"
 #include "rn_bp4.cuh"
+#ifndef RN_BP4_COOP
+#define RN_BP4_COOP 0   // 1: non-first sweeps with the gathers / REDs of the rays of a CTA issued together (rn_bp4c.cuh; measured slower)
+#endif
+#if RN_BP4_COOP
+#include "rn_bp4c.cuh"
+#endif
 #include "rn_parity.cuh"
 #include "rn_backward.cuh"
 #include "rn_peer.cuh"
@@ -288,6 +294,17 @@ int launch_bp2(const RnDev &d, Bp2Args a, bool first_sweep, int nch_max, cudaStr
 template <int NCH, bool kFirst>
 int launch_bp4_nf(const RnDev &d, Bp2Args a, cudaStream_t st) {
     constexpr int WARPS = rn_bp4_warps(NCH);
+#if RN_BP4_COOP
+    if constexpr (!kFirst) {
+        const size_t smem = (size_t)WARPS * rn_bp4c_warp_words(NCH, WARPS) * sizeof(float);
+        static SmemOptIn optc;
+        if (int rc = optc.ensure(bp4c_kernel<NCH>, smem, "bp4c_kernel")) return rc;
+        a.rays_per_warp = RN_BP4_RAYS_PER_WARP;
+        const int per_cta = WARPS * a.rays_per_warp;
+        bp4c_kernel<NCH><<<(unsigned)((a.n + per_cta - 1) / per_cta), 32 * WARPS, smem, st>>>(d, a);
+        return check_launch("bp4c_kernel");
+    }
+#endif
     const size_t smem = (size_t)WARPS * rn_bp4_warp_words(NCH, kFirst) * sizeof(float);
     static SmemOptIn opt;
     if (int rc = opt.ensure(bp4_kernel<NCH, kFirst>, smem, "bp4_kernel")) return rc;

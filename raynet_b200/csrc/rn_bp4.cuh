@@ -51,6 +51,9 @@ __device__ __forceinline__ float rn_occ_w2(float acc, float msg) {
     return (x >= 0.f) ? -u : u;
 }
 
+#ifndef RN_BP4_ABLATE
+#define RN_BP4_ABLATE 0        // 1 / 2: timing experiments without the REDs / the gathers (results are wrong)
+#endif
 #ifndef RN_BP4_RAYS_PER_WARP
 #define RN_BP4_RAYS_PER_WARP 8
 #endif
@@ -119,7 +122,11 @@ __device__ __forceinline__ void rn_bp4_ray(const float *acc_in, float *acc_out, 
             for (int j = 0; j < 4; j++) {
                 const int i = c * RN_CHUNK + 32 * j + lane;
                 ga[c][j] = 0.f;
+#if RN_BP4_ABLATE == 2   // timing experiment only: no accumulator gathers
+                if (c < NCH - 1 || i < L) ga[c][j] = (float)sLin[i] * 1e-12f;
+#else
                 if (c < NCH - 1 || i < L) ga[c][j] = rn_ld_acc_pol(acc_in + sLin[i], pol_keep);
+#endif
             }
         }
     }
@@ -220,7 +227,11 @@ __device__ __forceinline__ void rn_bp4_ray(const float *acc_in, float *acc_out, 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int i = c * RN_CHUNK + 32 * j + lane;
+#if RN_BP4_ABLATE == 1   // timing experiment only: no scatter-adds (the value still has to be produced)
+            if ((c < NCH - 1 || i < L) && sX[32 * j + lane] == 1.2345e-30f) rn_red_add_pol(acc_out + sLin[i], sX[32 * j + lane], pol_keep);
+#else
             if (c < NCH - 1 || i < L) rn_red_add_pol(acc_out + sLin[i], sX[32 * j + lane], pol_keep);
+#endif
         }
     }
 }

@@ -6,7 +6,8 @@ inference = gamma * (x - moving_mean) / sqrt(moving_variance + 1e-3) + beta; ReL
 four of the five blocks.  Everything in float64 (the comparison tolerance covers float32
 accumulation).  "parity unpinned": TensorFlow / Keras are not installed here and the reference has
 no test or fixture for its CNN; tests/test_oracle_pinning.py pins this file's convolution against an
-explicit loop restatement only.
+explicit loop restatement and the whole network against the same blocks written with torch's float64
+conv2d / batch_norm / relu (an independent second implementation, not the reference).
 """
 import numpy as np
 

@@ -271,6 +271,33 @@ def test_cnn_oracle_convolution_semantics():
     assert np.abs(cnn_np.conv3x3_valid(x, k, b) - ref).max() < 1e-12
 
 
+def test_cnn_oracle_vs_independent_library_network():
+    """The whole oracle network against the same five blocks written with another library's operators in float64
+    (torch.nn.functional.conv2d = cross-correlation on channels-first tensors, batch_norm in inference mode with
+    eps = 1e-3, relu).  Not the reference (Keras is not installed) -- an independent second implementation of the
+    layer semantics models.py:90-111 names; the CNN row stays "parity unpinned"."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import cnn_np
+    from raynet_b200.models import SimpleCNN
+    m = SimpleCNN.random_init(channels=3, seed=5)
+    weights = m.get_weights()
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0, 1, size=(2, 19, 23, 3))
+    ours = cnn_np.simple_cnn_forward(x, weights)
+    t = torch.from_numpy(x).permute(0, 3, 1, 2).double()
+    n_layers = len(weights) // 6
+    for l in range(n_layers):
+        k, b, g, be, mu, var = [torch.from_numpy(np.asarray(w)).double() for w in weights[6 * l:6 * l + 6]]
+        t = F.conv2d(t, k.permute(3, 2, 0, 1), b)                       # [kh][kw][cin][cout] -> [cout][cin][kh][kw]
+        t = F.batch_norm(t, mu, var, g, be, training=False, eps=1e-3)
+        if l < n_layers - 1:
+            t = F.relu(t)
+    theirs = t.permute(0, 2, 3, 1).numpy()
+    assert ours.shape == theirs.shape == (2, 9, 13, 32)
+    assert np.abs(ours - theirs).max() < 1e-12
+
+
 GOLDEN_PC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pointcloud_golden.npz")
 
 

@@ -576,7 +576,10 @@ def run_gpu_arm(args, cfg):
                                if not args.no_fuse else "separate mapping kernel",
                 "collective": ("sum of the per-rank partial f32[%d^3] accumulators after every sweep: %s" % (G, {
                     "peer": "this library's fused barrier + reduce + broadcast kernel over NVLink peer memory "
-                            "(rn_peer_allreduce_f32)"}.get(collective, "torch.distributed all_reduce, " + collective)))
+                            "(rn_peer_allreduce_f32)",
+                    "peer_multicast": "this library's fused exchange kernel, sum and broadcast inside the NVSwitch "
+                                      "(multimem.ld_reduce / multimem.st on the multicast addresses, "
+                                      "rn_peer_allreduce_mc_f32)"}.get(collective, "torch.distributed all_reduce, " + collective)))
                               if world > 1 else "none",
                 "l2": "per-step working set (%.1f GB of per-ray state on rank 0) is far larger than L2; no flush needed"
                       % (3 * n_rays * M * 4 / 1e9),
@@ -639,7 +642,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs only)")
     ap.add_argument("--no-fuse", action="store_true", help="separate plane->voxel mapping kernel instead of the fused first sweep")
     ap.add_argument("--no-balance", action="store_true", help="strong scaling: blocks of equal ray counts instead of equal work")
-    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "peer_p2p", "nccl"],
                     help="exchange step of the multi-GPU path (engine.py); auto = peer kernel when the GPUs map each other")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -387,6 +387,15 @@ int rn_peer_allreduce_f32(const uint64_t *peer_partials, const uint64_t *peer_re
                           float *zero_next_partial, int32_t rank, int32_t world, int32_t n_ctas, uint32_t epoch,
                           float prior, int64_t n, void *stream);
 
+/* The same exchange with the sum and the broadcast done inside the NVSwitch (NVLS): mc_partial / mc_result are the
+ * MULTICAST device addresses of the partial and result buffers (the multicast object bound to every rank's copy, e.g.
+ * the multicast_ptr of a torch symmetric-memory handle); one multimem.ld_reduce returns the sum over all ranks' partials,
+ * one multimem.st writes all ranks' results.  Everything else (flags, epoch, n_ctas, zero_next_partial, prior) as
+ * rn_peer_allreduce_f32.  The switch's addition order is unspecified: results agree with rn_peer_allreduce_f32 to
+ * float32 rounding, not bit for bit. */
+int rn_peer_allreduce_mc_f32(const float *mc_partial, float *mc_result, const uint64_t *peer_flags, float *zero_next_partial,
+                             int32_t rank, int32_t world, int32_t n_ctas, uint32_t epoch, float prior, int64_t n, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Plane->voxel mapping fused into the first sweep.  rn_engine_similarity = rn_engine_plane_scores (a2: plane-sweep
  * similarity + softmax -> S_planes float32 [n][depth_planes], feat_dim == 32 only) followed by rn_engine_map_planes

@@ -106,6 +106,7 @@ SIGNATURES = {
     "rn_conv3x3_bn_relu_tc": [_PTR] * 7 + [_I32] * 4 + [_PTR],
     # exchange step over NVLink peer memory
     "rn_peer_allreduce_f32": [_PTR, _PTR, _PTR, _PTR, _I32, _I32, _I32, ctypes.c_uint32, ctypes.c_float, _I64, _PTR],
+    "rn_peer_allreduce_mc_f32": [_PTR, _PTR, _PTR, _PTR, _I32, _I32, _I32, ctypes.c_uint32, ctypes.c_float, _I64, _PTR],
 }
 OTHER_SYMBOLS = ["rn_last_error", "rn_abi_version", "rn_device_info", "rn_code_stride", "rn_row_stride", "rn_num_classes",
                  "rn_brick_elems", "rn_backward_scratch_bytes"]

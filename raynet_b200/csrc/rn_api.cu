@@ -1072,6 +1072,29 @@ int rn_peer_allreduce_f32(const uint64_t *peer_partials, const uint64_t *peer_re
     return check_launch("peer_allreduce_kernel");
 }
 
+int rn_peer_allreduce_mc_f32(const float *mc_partial, float *mc_result, const uint64_t *peer_flags, float *zero_next_partial,
+                             int32_t rank, int32_t world, int32_t n_ctas, uint32_t epoch, float prior, int64_t n, void *stream) {
+    if (world < 1 || world > RN_PEER_MAX_WORLD || rank < 0 || rank >= world)
+        return fail(RN_ERR_UNSUPPORTED, "rn_peer_allreduce_mc_f32: world size must be in [1, %d]", RN_PEER_MAX_WORLD);
+    if (!mc_partial || !mc_result || !peer_flags) return fail(RN_ERR_SHAPE, "rn_peer_allreduce_mc_f32: NULL multicast address or flag table");
+    if (n <= 0 || (n & 3)) return fail(RN_ERR_SHAPE, "rn_peer_allreduce_mc_f32: n must be a positive multiple of 4");
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail(RN_ERR_CUDA, "rn_peer_allreduce_mc_f32: %s", cudaGetErrorString(e));
+    if (n_ctas < 1 || n_ctas > sms) return fail(RN_ERR_SHAPE, "rn_peer_allreduce_mc_f32: n_ctas must be in [1, %d] (all CTAs must be resident)", sms);
+    PeerArgs a = {};
+    for (int p = 0; p < world; p++) {
+        a.flags[p] = reinterpret_cast<uint32_t *>(peer_flags[p]);
+        if (!a.flags[p]) return fail(RN_ERR_SHAPE, "rn_peer_allreduce_mc_f32: NULL peer pointer");
+    }
+    a.mc_partial = mc_partial; a.mc_result = mc_result;
+    a.zero = zero_next_partial;
+    a.rank = rank; a.world = world; a.epoch = epoch; a.prior = prior; a.n = n;
+    peer_allreduce_mc_kernel<<<(unsigned)n_ctas, 512, 0, S(stream)>>>(a);
+    return check_launch("peer_allreduce_mc_kernel");
+}
+
 // ---- mapping fused into the first sweep (rn_first.cuh) ------------------------------------------------------------
 int rn_engine_plane_scores(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
                            const float *P, const float *starts, const float *ends, float *S_planes, int64_t n_rays,

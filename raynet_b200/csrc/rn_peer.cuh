@@ -30,6 +30,8 @@ struct PeerArgs {
     uint32_t epoch;                            // this call uses epoch + 1 and epoch + 2
     float prior;
     int64_t n;                                 // elements (multiple of 4)
+    const float *mc_partial;                   // multicast (NVLS) address of the partials / results: one load is reduced
+    float *mc_result;                          //   by the switch over all ranks, one store lands on all ranks
 };
 
 __device__ __forceinline__ void rn_st_release_sys(uint32_t *p, uint32_t v) {
@@ -107,6 +109,52 @@ __global__ void __launch_bounds__(512) peer_allreduce_kernel(PeerArgs a) {
             }
             for (int p = 0; p < world; p++) reinterpret_cast<float4 *>(a.result[(a.rank + p) % world])[i] = s;
         }
+    }
+    if (a.zero) {
+        float4 *z = reinterpret_cast<float4 *>(a.zero);
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) z[i] = zero4;
+    }
+    rn_peer_barrier(a, a.epoch + 2);
+}
+
+// ---- the same exchange with the reduction and the broadcast done INSIDE the NVSwitch (NVLS) ---------------------------
+// multimem.ld_reduce on the multicast address of the partials returns the sum over all ranks' copies, multimem.st on
+// the multicast address of the results writes all ranks' copies: a rank pulls its slice once (n / world elements in)
+// and pushes it once (n / world out) instead of world - 1 times each; every link carries n elements per direction
+// instead of 2 n (world - 1) / world.  Barriers, prior and fill as above.  The order in which the switch adds the
+// world operands is not specified: float32 sums differ from the peer-load kernel's in the last bit.
+__device__ __forceinline__ float4 rn_mc_ld_reduce4(const float *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rn_mc_st4(float *mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+#ifndef RN_PEER_MC_UNROLL
+#define RN_PEER_MC_UNROLL 4
+#endif
+__global__ void __launch_bounds__(512) peer_allreduce_mc_kernel(PeerArgs a) {
+    rn_peer_barrier(a, a.epoch + 1);
+    const int64_t n4 = a.n >> 2;
+    const int64_t per = (n4 + a.world - 1) / a.world;
+    const int64_t lo = per * a.rank, hi = min(n4, lo + per);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += RN_PEER_MC_UNROLL * stride) {
+        float4 v[RN_PEER_MC_UNROLL];
+#pragma unroll
+        for (int u = 0; u < RN_PEER_MC_UNROLL; u++)
+            if (i + u * stride < hi) v[u] = rn_mc_ld_reduce4(a.mc_partial + 4 * (i + u * stride));
+#pragma unroll
+        for (int u = 0; u < RN_PEER_MC_UNROLL; u++)
+            if (i + u * stride < hi) {
+                v[u].x += a.prior; v[u].y += a.prior; v[u].z += a.prior; v[u].w += a.prior;
+                rn_mc_st4(a.mc_result + 4 * (i + u * stride), v[u]);
+            }
     }
     if (a.zero) {
         float4 *z = reinterpret_cast<float4 *>(a.zero);

@@ -69,7 +69,8 @@ class RayPotentialEngine(object):
         per-ray state may take (default: 85 % of the free memory at construction).
         max_segment_rays: upper bound on the rays of one segment (default H * W).
         collective: how the per-rank partial accumulators are summed after a sweep when world > 1 --
-        "peer": this library's fused exchange kernel over NVLink peer memory (sharding.PeerExchange),
+        "peer": this library's fused exchange kernel over NVLink peer memory (sharding.PeerExchange; with the sum and
+        the broadcast done inside the NVSwitch where the fabric offers multicast, "peer_p2p" keeps it on peer loads),
         "nccl": torch.distributed all_reduce, "auto": peer when the GPUs can map each other's memory
         (float32 accumulators only), else nccl; self.collective says which one runs.
         fuse_first_sweep: score_image() only computes the plane distributions; the FIRST sweep after a reset
@@ -122,14 +123,14 @@ class RayPotentialEngine(object):
         self.collective = "none"
         self._peer = None
         if self.world > 1:
-            assert collective in ("auto", "peer", "nccl")
+            assert collective in ("auto", "peer", "peer_p2p", "nccl")
             self.collective = "nccl"
-            if collective in ("auto", "peer") and not self.parity:
+            if collective in ("auto", "peer", "peer_p2p") and not self.parity:
                 try:
-                    self._peer = sharding.PeerExchange(self.GB, self.dev, self.pg)
-                    self.collective = "peer"
+                    self._peer = sharding.PeerExchange(self.GB, self.dev, self.pg, multicast=(False if collective == "peer_p2p" else None))
+                    self.collective = "peer_multicast" if self._peer.multicast else "peer"
                 except RuntimeError as e:
-                    if collective == "peer":
+                    if collective != "auto":
                         raise
                     self.collective = "nccl (%s)" % (e,)
         if self._peer is not None:

@@ -129,7 +129,7 @@ class PeerExchange(object):
     `ex.partial` to it, so no fill is launched between sweeps; reset() zeroes the current one.
     Raises RuntimeError when the GPUs cannot map each other's memory (the caller then stays on NCCL)."""
 
-    def __init__(self, n, device, group=None, n_ctas=None):
+    def __init__(self, n, device, group=None, n_ctas=None, multicast=None):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
@@ -141,7 +141,7 @@ class PeerExchange(object):
         self.n = int(n)
         assert self.n % 4 == 0
         sms = torch.cuda.get_device_properties(device).multi_processor_count
-        self.n_ctas = int(n_ctas or sms)
+        self.n_ctas = int(n_ctas or sms)      # (multicast kernel: 64 CTAs measured best, see below)
         try:
             self._partials = [symm_mem.empty(self.n, dtype=torch.float32, device=device) for _ in range(2)]
             self.result = symm_mem.empty(self.n, dtype=torch.float32, device=device)
@@ -154,6 +154,19 @@ class PeerExchange(object):
             raise RuntimeError("peer-mapped accumulators unavailable: %r" % (e,))
         self._handles = handles     # keep the mappings alive
         self._tables = [(ctypes.c_uint64 * self.world)(*[int(p) for p in h.buffer_ptrs]) for h in handles]
+        # multicast (NVLS) addresses of the partials and the result: the switch then sums / broadcasts (rn_peer.cuh);
+        # 0 where the fabric has no multicast support -- the peer-load kernel runs instead
+        try:
+            self._mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in handles[:3]]
+        except Exception:
+            self._mc = [0, 0, 0]
+        # None: where it moves fewer bytes per link -- n (1 + 1 / world) against 2 n (world - 1) / world for peer loads,
+        # measured for the 64 MiB grid of C3: 2 ranks 0.196 against 0.128 ms, 4 ranks 0.178 against 0.173 ms, 8 ranks
+        # 0.174 against 0.221 ms (profiles/r02_exchange_microbench.json) -> beyond 4 ranks
+        want = (self.world > 4) if multicast is None else bool(multicast)
+        self.multicast = want and all(self._mc)
+        if self.multicast and n_ctas is None:
+            self.n_ctas = min(self.n_ctas, 64)      # 0.174 ms with 64 CTAs, 0.186 ms with 148 (8 GPUs, 64 MiB)
         self.cur = 0
         self.epoch = 0
         torch.cuda.synchronize(device)
@@ -165,9 +178,14 @@ class PeerExchange(object):
 
     def allreduce(self, prior):
         nxt = self.cur ^ 1
-        self._lib.call("rn_peer_allreduce_f32", self._tables[self.cur], self._tables[2], self._tables[3],
-                       self._partials[nxt].data_ptr(), self.rank, self.world, self.n_ctas,
-                       ctypes.c_uint32(self.epoch & 0xffffffff), float(prior), self.n, self._stream())
+        if self.multicast:
+            self._lib.call("rn_peer_allreduce_mc_f32", self._mc[self.cur], self._mc[2], self._tables[3],
+                           self._partials[nxt].data_ptr(), self.rank, self.world, self.n_ctas,
+                           ctypes.c_uint32(self.epoch & 0xffffffff), float(prior), self.n, self._stream())
+        else:
+            self._lib.call("rn_peer_allreduce_f32", self._tables[self.cur], self._tables[2], self._tables[3],
+                           self._partials[nxt].data_ptr(), self.rank, self.world, self.n_ctas,
+                           ctypes.c_uint32(self.epoch & 0xffffffff), float(prior), self.n, self._stream())
         self.epoch += 2
         self.cur = nxt
         return self.result

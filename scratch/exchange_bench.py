@@ -1,4 +1,4 @@
-"""Times the accumulator exchange alone (64 MiB float32 grid of C3): this library's peer kernel at several CTA counts
+"""(run by scripts/gpu_multi.sh) Times the accumulator exchange alone (64 MiB float32 grid of C3): this library's peer kernel at several CTA counts
 vs torch.distributed.all_reduce (NCCL), under torchrun."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,9 +27,13 @@ def timed(fn, reps=40):
 
 x = torch.zeros(n, device=dev)
 out["nccl_all_reduce_ms"] = timed(lambda: dist.all_reduce(x))
-for ctas in (148, 96, 64, 32):
-    ex = sharding.PeerExchange(n, dev, n_ctas=ctas)
-    out["peer_%d_ctas_ms" % ctas] = timed(lambda: ex.allreduce(-2.9))
+for ctas, mc in ((148, True), (96, True), (64, True), (32, True), (148, False), (96, False)):
+    ex = sharding.PeerExchange(n, dev, n_ctas=ctas, multicast=mc)
+    if mc and not ex.multicast:
+        out["multicast"] = "unavailable"
+        del ex
+        continue
+    out["peer_%s_%d_ctas_ms" % ("multicast" if mc else "p2p", ctas)] = timed(lambda: ex.allreduce(-2.9))
     # correctness: every partial holds rank + 1 -> result = prior + world (world + 1) / 2
     ex.partial.fill_(float(rank + 1)); torch.cuda.synchronize(); dist.barrier()
     r = ex.allreduce(0.5); torch.cuda.synchronize()

@@ -44,6 +44,7 @@ def main():
                               max_number_of_marched_voxels=M, padding=11, gamma_mrf=0.05)
     out = {}
     for name, model, coll in (("features", FeatureModel(), "auto"), ("features_nccl", FeatureModel(), "nccl"),
+                              ("features_p2p", FeatureModel(), "peer_p2p"),
                               ("cnn", SimpleCNN.random_init(channels=3, seed=1), "auto")):
         sharded = RayNetForwardPass(model, gp, "sample_in_bbox", scene.image_shape, H * W, bp_iterations=I, shard="rays",
                                     collective=coll)

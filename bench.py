@@ -599,8 +599,8 @@ def run_gpu_arm(args, cfg):
                 "all_sweeps": {"algorithmic_bytes": blend_bytes, "ms": blend_ms, "frac": frac(blend_bytes, blend_ms)},
                 "stages": {
                     "frontend": {"algorithmic_bytes": fe_bytes, "ms": fe_ms, "frac": frac(fe_bytes, fe_ms),
-                                 "note": "bound by L2 -> SM gather bandwidth, not HBM: every (ray, plane, view) sample "
-                                         "is its own 128-byte feature vector (DESIGN.md 4)"},
+                                 "note": "not an HBM-bound stage: every (ray, plane, view) sample is its own 128-byte feature vector, "
+                                         "gathered through the L1 (L1 data pipe 65 % busy, issue 58 %; DESIGN.md 4)"},
                     "bp": {"algorithmic_bytes": blend_bytes + grid_bytes, "ms": bp_ms, "frac": frac(blend_bytes + grid_bytes, bp_ms)},
                     "depth": {"algorithmic_bytes": de_bytes, "ms": de_ms, "frac": frac(de_bytes, de_ms)},
                 },

@@ -17,10 +17,11 @@ dump() {  # name mangled
 }
 dump bp4_nch4_next _Z10bp4_kernelILi4ELb0EEv5RnDev7Bp2Args
 dump bp4_nch3_first _Z10bp4_kernelILi3ELb1EEv5RnDev7Bp2Args
-dump simscore3_v9 _Z16simscore3_kernelILi9EEv5RnDev10SimMapArgs
+dump simscore3_v9 _Z16simscore3_kernelILi9ELi16EEv5RnDev10SimMapArgs
 dump planemap3 _Z16planemap3_kernel5RnDev10SimMapArgs
 dump depth3 _Z13depth3_kernel5RnDev10Depth2Args
-dump peer_allreduce _Z21peer_allreduce_kernel8PeerArgs
+dump peer_allreduce _Z21peer_allreduce_kernelILi8EEv8PeerArgs
+dump peer_allreduce_mc _Z24peer_allreduce_mc_kernel8PeerArgs
 dump bp_parity _Z16bp_parity_kernelILb0EEv5RnDev10ParityArgs
 dump bp4_first_mapped_nch4 _Z23bp4_first_mapped_kernelILi4EEv5RnDev9FirstArgs
 dump conv3x3_tc _Z17conv3x3_tc_kernel14CUtensorMap_stS_10ConvTcArgs

@@ -952,7 +952,7 @@ int rn_bp_sweep_backward(const RnParams *p, const float *S, const int32_t *ray_v
     for (int64_t first = 0; first < n_rays; first += chunk) {
         a.first = first;
         a.n = (n_rays - first < chunk) ? n_rays - first : chunk;
-        bp_sweep_bwd_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, S_(stream)>>>(d, a);
+        bp_sweep_bwd_kernel<<<(unsigned)((a.n + 3) / 4), 128, 0, S_(stream)>>>(d, a);
         if ((rc = check_launch("bp_sweep_bwd_kernel"))) return rc;
     }
     return RN_OK;
@@ -976,7 +976,7 @@ int rn_depth_estimate_backward(const RnParams *p, const float *S, const int32_t 
     for (int64_t first = 0; first < n_rays; first += chunk) {
         a.first = first;
         a.n = (n_rays - first < chunk) ? n_rays - first : chunk;
-        depth_bwd_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, S_(stream)>>>(d, a);
+        depth_bwd_kernel<<<(unsigned)((a.n + 3) / 4), 128, 0, S_(stream)>>>(d, a);
         if ((rc = check_launch("depth_bwd_kernel"))) return rc;
     }
     return RN_OK;
@@ -1001,7 +1001,7 @@ int rn_planes_to_voxels_backward(const RnParams *p, const float *voxel_grid, con
     a.S_planes = S_planes; a.g_s_norm = g_in; a.g_is_raw = g_is_wrt_S_voxel_space ? 1 : 0;
     a.g_S_vox = g_S_voxel_space; a.g_S = g_S_planes; a.g_scores = g_scores;
     a.n = n_rays;
-    frontend_bwd_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, S_(stream)>>>(d, a);
+    frontend_bwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, S_(stream)>>>(d, a);
     rc = check_launch("frontend_bwd_kernel");
     scratch_free(axes, S_(stream));
     return rc;
@@ -1013,7 +1013,7 @@ int rn_clip_renorm_backward(const RnParams *p, const float *S, const int32_t *ra
     int rc = make_dev(p, d, true, false, false);
     if (rc) return rc;
     if (n_rays <= 0) return RN_OK;
-    clip_renorm_bwd_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, S_(stream)>>>(d, S, ray_voxel_count, g_s_norm, g_S, n_rays);
+    clip_renorm_bwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, S_(stream)>>>(d, S, ray_voxel_count, g_s_norm, g_S, n_rays);
     return check_launch("clip_renorm_bwd_kernel");
 }
 
@@ -1035,7 +1035,7 @@ int rn_depth_loss(const RnParams *p, int32_t kind, const float *y_true, const fl
         if (rc) return rc;
         a.idx = ray_voxel_indices; a.axes = axes; a.centres = camera_centres;
     }
-    depth_loss_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, S_(stream)>>>(d, a);
+    depth_loss_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, S_(stream)>>>(d, a);
     rc = check_launch("depth_loss_kernel");
     scratch_free(axes, S_(stream));
     return rc;

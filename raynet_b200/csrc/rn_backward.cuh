@@ -41,7 +41,7 @@ struct BwdArgs {
     float *g_s;                // [n][M] += gradient w.r.t. S_norm
     float *g_msg_in;           // [n][M]  = gradient w.r.t. msg_in (may alias g_out)
     float *g_acc_in;           // [G]    += gradient w.r.t. acc_in (atomic)
-    double *scratch;           // [slots][M][n_chunk]
+    double *scratch;           // [n_chunk][slots][M]
     int64_t first, n;          // rays [first, first + n) of the arrays above
 };
 

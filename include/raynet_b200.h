@@ -408,6 +408,15 @@ int rn_peer_allreduce_mc_f32(const float *mc_partial, float *mc_result, const ui
 int rn_engine_plane_scores(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
                            const float *P, const float *starts, const float *ends, float *S_planes, int64_t n_rays,
                            void *stream);
+
+/* rn_engine_plane_scores with an explicit plane schedule.  planes_per_pass: 0 = every ray scores all its depth planes
+ * in one pass; k > 0 = the planes are swept in blocks of k, each block over all n_rays (the feature vectors a block
+ * touches stay L2-resident when the views' feature maps are many times the L2), the softmax once at the end -- the
+ * result is bit-identical; < 0 = chosen by the library, which is what rn_engine_plane_scores does (currently always
+ * the single pass: the blocked sweep measured slower on the 2 GB feature maps of BASELINE.json configs[4]). */
+int rn_engine_plane_scores_passes(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
+                                  const float *P, const float *starts, const float *ends, float *S_planes, int64_t n_rays,
+                                  int32_t planes_per_pass, void *stream);
 int rn_engine_map_planes(const RnParams *p, const float *axis_centres, const float *starts, const float *ends,
                          const uint32_t *ray_hdr, const uint8_t *codes, const int32_t *count, const float *S_planes,
                          float *s_hat, int32_t *lin, int64_t n_rays, void *stream);

@@ -99,6 +99,7 @@ SIGNATURES = {
     "rn_depth_loss": [_PP, _I32] + [_PTR] * 7 + [ctypes.c_float, _I64, _PTR],
     # mapping fused into the first sweep
     "rn_engine_plane_scores": [_PP, _PTR, _PTR, _I32] + [_PTR] * 4 + [_I64, _PTR],
+    "rn_engine_plane_scores_passes": [_PP, _PTR, _PTR, _I32] + [_PTR] * 4 + [_I64, _I32, _PTR],
     "rn_engine_map_planes": [_PP] + [_PTR] * 9 + [_I64, _PTR],
     "rn_engine_first_sweep_mapped": [_PP] + [_PTR] * 14 + [_I64, _PTR],
     # MV-CNN on the tensor cores

@@ -197,16 +197,13 @@ int launch_simscore3_w(const RnDev &d, const SimMapArgs &a, cudaStream_t st) {
 template <int VT>
 int launch_simscore3(const RnDev &d, const SimMapArgs &a, cudaStream_t st) {
 #if RN_SIMSCORE_WIDE > 0
-    if (a.tile_len > 0 && (32 / RN_SIMSCORE_WIDE) * (simscore3_smem(d, RN_SIMSCORE_WIDE) + 1024) <= 200 * 1024)
+    if (a.tile_len > 0 && (rn_simscore_warps_per_sm(VT) / RN_SIMSCORE_WIDE) * (simscore3_smem(d, RN_SIMSCORE_WIDE) + 1024) <= 200 * 1024)
         return launch_simscore3_w<VT, RN_SIMSCORE_WIDE>(d, a, st);
 #endif
     return launch_simscore3_w<VT, 4>(d, a, st);
 }
 
-int launch_plane_scores(const RnDev &d, SimMapArgs a, cudaStream_t st) {
-    if (a.n_rays <= 0) return RN_OK;
-    a.tile_len = tile_len_for(d, a.n_rays);
-    a.tile_mode = 2;
+int launch_plane_scores_pass(const RnDev &d, const SimMapArgs &a, cudaStream_t st) {
     switch (d.V) {   // common view counts get fully unrolled loops
         case 3: return launch_simscore3<3>(d, a, st);
         case 5: return launch_simscore3<5>(d, a, st);
@@ -216,6 +213,31 @@ int launch_plane_scores(const RnDev &d, SimMapArgs a, cudaStream_t st) {
         case 15: return launch_simscore3<15>(d, a, st);
     }
     return launch_simscore3<0>(d, a, st);
+}
+
+// planes_per_pass: 0 = all planes of a ray in one pass; > 0 = the planes are swept in blocks of that many, every
+// block over ALL rays of the call, the softmax once at the end (bit-identical result); < 0 = chosen here.
+// The blocked sweep was built for feature maps many times the L2 (C5: 2 GB of maps per rank against 126 MB; a block
+// of planes of a patch of rays reads a short piece of each epipolar band instead of the whole band).  Measured on the
+// C5 workload of one GPU, front end per step: single pass 46.2 ms, blocks of 32 planes 56.7 ms (16-ray CTAs), 58.9 ms
+// both ways with 4-ray CTAs -- the kernel is not bound by L2 misses, so the library never picks it on its own.
+int launch_plane_scores(const RnDev &d, SimMapArgs a, cudaStream_t st, int planes_per_pass = -1) {
+    if (a.n_rays <= 0) return RN_OK;
+    a.tile_len = tile_len_for(d, a.n_rays);
+    a.tile_mode = 2;
+    if (planes_per_pass < 0) planes_per_pass = 0;
+    if (planes_per_pass <= 0 || planes_per_pass >= d.D || d.D > 128) {
+        a.k_lo = a.k_hi = 0; a.raw_scores = 0;
+        return launch_plane_scores_pass(d, a, st);
+    }
+    a.raw_scores = 1;
+    for (int k = 0; k < d.D; k += planes_per_pass) {
+        a.k_lo = k;
+        a.k_hi = (k + planes_per_pass < d.D) ? k + planes_per_pass : d.D;
+        if (int rc = launch_plane_scores_pass(d, a, st)) return rc;
+    }
+    softmax_planes_kernel<<<(unsigned)((a.n_rays + 3) / 4), 128, 0, st>>>(a.S_planes, a.n_rays, d.D);
+    return check_launch("softmax_planes_kernel");
 }
 
 int launch_planemap3(const RnDev &d, SimMapArgs a, cudaStream_t st) {
@@ -1096,9 +1118,9 @@ int rn_peer_allreduce_mc_f32(const float *mc_partial, float *mc_result, const ui
 }
 
 // ---- mapping fused into the first sweep (rn_first.cuh) ------------------------------------------------------------
-int rn_engine_plane_scores(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
-                           const float *P, const float *starts, const float *ends, float *S_planes, int64_t n_rays,
-                           void *stream) {
+int rn_engine_plane_scores_passes(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
+                                  const float *P, const float *starts, const float *ends, float *S_planes, int64_t n_rays,
+                                  int32_t planes_per_pass, void *stream) {
     RnDev d;
     int rc = make_dev(p, d, true, true, true);
     if (rc) return rc;
@@ -1110,7 +1132,13 @@ int rn_engine_plane_scores(const RnParams *p, const float *features, const int32
     SimMapArgs a = {};
     a.starts_in = starts; a.ends_in = ends; a.features = features; a.view_ids = view_ids; a.P = P;
     a.S_planes = S_planes; a.n_rays = n_rays;
-    return launch_plane_scores(d, a, S(stream));
+    return launch_plane_scores(d, a, S(stream), planes_per_pass);
+}
+
+int rn_engine_plane_scores(const RnParams *p, const float *features, const int32_t *view_ids, int32_t n_feature_slots,
+                           const float *P, const float *starts, const float *ends, float *S_planes, int64_t n_rays,
+                           void *stream) {
+    return rn_engine_plane_scores_passes(p, features, view_ids, n_feature_slots, P, starts, ends, S_planes, n_rays, -1, stream);
 }
 
 int rn_engine_map_planes(const RnParams *p, const float *axis_centres, const float *starts, const float *ends,

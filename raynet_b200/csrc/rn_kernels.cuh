@@ -138,6 +138,8 @@ struct SimMapArgs {
     int64_t tile_len;          // > 0: warps walk the rays in 8x8-pixel tiles (rn_tiled_position)
     int val_stride;            // floats of the per-warp voxel buffer (0 without mapping stage)
     int tile_mode;
+    int k_lo, k_hi;            // simscore3_kernel: planes [k_lo, k_hi) of this pass (k_hi == 0: all D planes)
+    int raw_scores;            // simscore3_kernel: 1 = store the plane scores of the pass, softmax by softmax_planes_kernel
 };
 
 // dynamic shared memory: per CTA [V*12 P][12 P_inv][4 C][V view slots], per warp

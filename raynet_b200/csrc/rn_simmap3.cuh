@@ -80,8 +80,8 @@ __device__ __forceinline__ int rn_feature_offset(const RnDev &p, int base, int f
 // seeds the accumulators; separate instantiations keep predicated copies out of the loop.
 template <int VT, bool kRef>
 __device__ __forceinline__ void rn_plane_scores(const RnDev &p, const SimMapArgs &a, const int *sOff, float *sS,
-                                                int ref_off, int lane) {
-    const int D = p.D, V = VT ? VT : p.V, VP = (V + 3) & ~3;
+                                                int ref_off, int lane, const int D /* planes of this pass */) {
+    const int V = VT ? VT : p.V, VP = (V + 3) & ~3;
     const float inv_pairs = 0.5f / (float)p.npairs;
     const int g = lane >> 3;
     const char *featb = reinterpret_cast<const char *>(a.features) + (lane & 7) * 16;
@@ -163,8 +163,15 @@ __device__ __forceinline__ int64_t rn_simscore_slot(int64_t cta, int wid, int64_
     return (t & ~(int64_t)63) | (xo << 3) | yo;
 }
 
+// Warps per SM the register budget is set for: 32 (<= 64 registers) up to 11 views; beyond that the V gathers of two
+// plane groups no longer fit in 64 registers (15 views: spills, loads serialised) -- 16 warps at <= 128 registers.
+#ifndef RN_SIMSCORE_MANY_VIEWS
+#define RN_SIMSCORE_MANY_VIEWS 12
+#endif
+__host__ __device__ constexpr int rn_simscore_warps_per_sm(int vt) { return (vt >= RN_SIMSCORE_MANY_VIEWS) ? 16 : 32; }
+
 template <int VT, int kW>
-__global__ void __launch_bounds__(32 * kW, 32 / kW) simscore3_kernel(RnDev p, SimMapArgs a) {   // 32 warps per SM at <= 64 registers
+__global__ void __launch_bounds__(32 * kW, rn_simscore_warps_per_sm(VT) / kW) simscore3_kernel(RnDev p, SimMapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = p.D, V = VT ? VT : p.V;   // VT > 0: compile-time view count, loops fully unrolled
@@ -183,6 +190,9 @@ __global__ void __launch_bounds__(32 * kW, 32 / kW) simscore3_kernel(RnDev p, Si
 
     const float fDm1 = (float)(D - 1);
     const int fshift = p.shift;
+    // planes of this pass (all of them unless the launcher sweeps the planes in blocks, see launch_plane_scores)
+    const int k_lo = a.k_hi > 0 ? a.k_lo : 0, k_hi = a.k_hi > 0 ? a.k_hi : D;
+    const int Dl = k_hi - k_lo;
 
     const int64_t t = rn_simscore_slot<kW>(blockIdx.x, wid, a.tile_len);
     if (!RN_SIMSCORE_SYNC && t >= a.n_rays) return;
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(32 * kW, 32 / kW) simscore3_kernel(RnDev p, Si
     const int VP = (V + 3) & ~3;
     bool ref_same = true;   // all samples of view 0 land on one pixel (the reference view)
     int ref_off = 0;
-    for (int kb = 0; kb < D; kb += 64) {
+    for (int kb = k_lo; kb < k_hi; kb += 64) {
         const int kk[2] = {kb + lane, kb + 32 + lane};
         float pt[2][3];
 #pragma unroll
@@ -234,10 +244,10 @@ __global__ void __launch_bounds__(32 * kW, 32 / kW) simscore3_kernel(RnDev p, Si
                     fy = (int)(roundf(o1 / nz) + (float)fshift);
                 }
                 const int off = (int)((uint32_t)rn_feature_offset(p, vbase, fx, fy) * 4u);   // BYTE offset (feature volume < 4 GiB)
-                if (kk[h] < D) {
-                    sOff[kk[h] * VP + v] = off;   // (16-byte stores of a plane's offsets, conflict-free, measured slower: 12.55 vs 11.94 ms)
+                if (kk[h] < k_hi) {
+                    sOff[(kk[h] - k_lo) * VP + v] = off;   // (16-byte stores of a plane's offsets, conflict-free, measured slower: 12.55 vs 11.94 ms)
                     if (v == 0) {
-                        if (kk[h] == lane) ref_off = off;
+                        if (kk[h] == k_lo + lane) ref_off = off;
                         else if (off != ref_off) ref_same = false;
                     }
                 }
@@ -246,15 +256,20 @@ __global__ void __launch_bounds__(32 * kW, 32 / kW) simscore3_kernel(RnDev p, Si
     }
     {
         const int off0 = __shfl_sync(RN_FULL_MASK, ref_off, 0);
-        ref_same = __all_sync(RN_FULL_MASK, ref_same && (lane >= D || ref_off == off0));
+        ref_same = __all_sync(RN_FULL_MASK, ref_same && (lane >= Dl || ref_off == off0));
         ref_off = off0;
     }
     __syncwarp();
 
     // ---- step 2: plane scores S_k = 1/2 (|sum_v f_v|^2 - sum_v |f_v|^2) / pairs ----------------------
-    if (ref_same) rn_plane_scores<VT, true>(p, a, sOff, sS, ref_off, lane);
-    else rn_plane_scores<VT, false>(p, a, sOff, sS, ref_off, lane);
+    if (ref_same) rn_plane_scores<VT, true>(p, a, sOff, sS, ref_off, lane, Dl);
+    else rn_plane_scores<VT, false>(p, a, sOff, sS, ref_off, lane, Dl);
     __syncwarp();
+    if (a.raw_scores) {   // plane-blocked sweep: the softmax follows once every block is in (softmax_planes_kernel)
+        if (live)
+            for (int k = lane; k < Dl; k += 32) a.S_planes[r * (int64_t)D + k_lo + k] = sS[k];
+        return;
+    }
 
     // ---- step 3: softmax over the D planes (feature_similarities.cu:109-123) --------------------------
     float mx = -INFINITY;
@@ -269,6 +284,33 @@ __global__ void __launch_bounds__(32 * kW, 32 / kW) simscore3_kernel(RnDev p, Si
     ssum = rn_warp_sum(ssum);
     if (live)
         for (int k = lane; k < D; k += 32) a.S_planes[r * (int64_t)D + k] = sS[k] / ssum;
+}
+
+// Softmax over the D plane scores of every ray, in place (feature_similarities.cu:109-123) -- step 3 of
+// simscore3_kernel as its own kernel for the plane-blocked sweep; the same lane assignment and operation order, so
+// the result is bit-identical to the single-pass kernel's.
+__global__ void __launch_bounds__(128) softmax_planes_kernel(float *S_planes, int64_t n_rays, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (r >= n_rays) return;
+    float *row = S_planes + r * (int64_t)D;
+    float mx = -INFINITY;
+    for (int k = lane; k < D; k += 32) mx = fmaxf(mx, row[k]);
+    mx = rn_warp_max(mx);
+    float ssum = 0.f;
+    float ev[4];   // D <= 128
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int k = lane + 32 * j;
+        ev[j] = (k < D) ? expf(row[k] - mx) : 0.f;
+        if (k < D) ssum += ev[j];
+    }
+    ssum = rn_warp_sum(ssum);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int k = lane + 32 * j;
+        if (k < D) row[k] = ev[j] / ssum;
+    }
 }
 
 // a4: plane -> voxel mapping (planes_voxels_mapping.cu:6-92) + clip_and_renorm (mrf_np.py:4-8) from

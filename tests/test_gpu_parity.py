@@ -189,6 +189,27 @@ def test_similarity_vs_oracle(torch_cuda, lib, oracle, mk):
     assert np.array_equal(S2.cpu().numpy(), S)
 
 
+@pytest.mark.parametrize("V,D,planes", [(9, 64, 32), (9, 64, 8), (5, 24, 5), (15, 40, 32), (6, 33, 16)])
+def test_plane_blocked_similarity_is_bit_identical(torch_cuda, lib, oracle, V, D, planes):
+    """rn_engine_plane_scores_passes: the planes swept in blocks over all rays (the schedule chosen for feature maps
+    far larger than L2) against the single pass -- bit-identical distributions -- and against the oracle.
+    Whole 8-pixel column groups (the tiled ray enumeration and the 16-ray CTAs) and a ragged ray subset."""
+    torch = torch_cuda
+    for n_rays in (None, 1000):
+        c = Case(32, V, D, 32, 40, 96, n_rays=n_rays, seed=3)
+        p = _params(lib, c)
+        o = _oracle_frontend(oracle, c)
+        out = []
+        for ppp in (0, planes):
+            S = torch.full((c.N, c.D), -1.0, dtype=torch.float32, device="cuda")
+            lib.call("rn_engine_plane_scores_passes", p, _d(torch, c.features).data_ptr(), None, 0, _d(torch, c.P).data_ptr(),
+                     _d(torch, o["starts"]).data_ptr(), _d(torch, o["ends"]).data_ptr(), S.data_ptr(), c.N, ppp,
+                     _stream(torch))
+            out.append(S.cpu().numpy())
+        assert np.array_equal(out[0], out[1])
+        assert np.abs(out[1] - o["S"]).max() <= TOL_P
+
+
 def test_similarity_with_depth_and_points(torch_cuda, lib, oracle):
     """rn_mvcnn_forward_depth: D points per ray + |point[argmax S] - C| (similarities.py:168-230)."""
     torch = torch_cuda

@@ -499,7 +499,7 @@ int rn_planes_to_voxels(const RnParams *p, const float *voxel_grid, const int32_
     float *axes = nullptr;
     rc = axes_from_voxel_grid(d, voxel_grid, &axes, S(stream));
     if (rc) return rc;
-    planes_to_voxels_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, S(stream)>>>(d, axes, ray_voxel_indices, ray_voxel_count, starts, ends, S_in, S_new, n_rays);
+    planes_to_voxels_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, S(stream)>>>(d, axes, ray_voxel_indices, ray_voxel_count, starts, ends, S_in, S_new, n_rays);
     rc = check_launch("planes_to_voxels");
     scratch_free(axes, S(stream));
     return rc;

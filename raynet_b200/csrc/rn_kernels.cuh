@@ -513,12 +513,15 @@ __global__ void sample_points_kernel(RnDev p, const int32_t *ids, const float *P
     }
 }
 
-// Stand-alone a4 on precomputed S (planes_voxels_mapping.cu:6-118): thread per ray,
-// sequential over the ray with the reference's persistent two-pointer bracket.
-__global__ void planes_to_voxels_kernel(RnDev p, const float *axes, const int32_t *idx, const int32_t *cnt,
-                                        const float *starts, const float *ends, const float *S, float *S_new,
-                                        int64_t n) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Stand-alone a4 on precomputed S (planes_voxels_mapping.cu:6-118): warp per ray, a lane per voxel.  The reference
+// walks two persistent plane pointers along the ray; t never decreases along a ray (every DDA step moves the voxel
+// centre along the ray's own direction), so they stop at the smallest right >= 1 whose float test
+// t - right * step <= 0 holds -- found per voxel from ceil(t / step) with the SAME float expressions deciding.
+__global__ void __launch_bounds__(128) planes_to_voxels_kernel(RnDev p, const float *axes, const int32_t *idx, const int32_t *cnt,
+                                                               const float *starts, const float *ends, const float *S, float *S_new,
+                                                               int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (r >= n) return;
     const int L = cnt[r];
     const int32_t *row = idx + r * (int64_t)p.M * 3;
@@ -529,25 +532,22 @@ __global__ void planes_to_voxels_kernel(RnDev p, const float *axes, const int32_
     float ray_norm = 0.f;
     for (int i = 0; i < 3; i++) ray_norm += ray[i] * ray[i];
     const float step = (1.0f - 0.0f) / (float)(p.D - 1);
-    int left = 0, right = 1;
-    float srsum = 0.f;
-    for (int i = 0; i < L; i++) {
+    float part = 0.f;
+    for (int i = lane; i < L; i += 32) {
         float cc[3] = {axes[row[3 * i]], axes[p.gx + row[3 * i + 1]], axes[p.gx + p.gy + row[3 * i + 2]]};
         float sum = 0.f;
         for (int j = 0; j < 3; j++) { float vd = cc[j]; vd -= rs[j]; sum += ray[j] * vd; }
-        float t = rn_clampf(sum / ray_norm, 1e-4f, 1 - 1e-4f);
-        float left_d = t - (0.0f + (float)left * step), right_d = t - (0.0f + (float)right * step);
-        while (left_d > 0 && right_d > 0) {
-            left++; right++;
-            left_d = t - (0.0f + (float)left * step);
-            right_d = t - (0.0f + (float)right * step);
-        }
-        left_d = fabsf(left_d); right_d = fabsf(right_d);
-        float c1 = (float)(1.0 - (double)(left_d / (left_d + right_d)));
-        float c2 = (float)(1.0 - (double)(right_d / (left_d + right_d)));
-        float v = c1 * Sr[left] + c2 * Sr[right];
+        const float t = rn_clampf(sum / ray_norm, 1e-4f, 1 - 1e-4f);
+        int right = min(max((int)ceilf(t / step), 1), p.D - 1);
+        while (right > 1 && t - (0.0f + (float)(right - 1) * step) <= 0) right--;
+        while (right < p.D - 1 && t - (0.0f + (float)right * step) > 0) right++;
+        const float left_d = fabsf(t - (0.0f + (float)(right - 1) * step)), right_d = fabsf(t - (0.0f + (float)right * step));
+        const float c1 = (float)(1.0 - (double)(left_d / (left_d + right_d)));
+        const float c2 = (float)(1.0 - (double)(right_d / (left_d + right_d)));
+        const float v = c1 * Sr[right - 1] + c2 * Sr[right];
         out[i] = v;
-        srsum += v;
+        part += v;
     }
-    for (int i = 0; i < L; i++) out[i] = out[i] / srsum;
+    const float srsum = rn_warp_sum(part);
+    for (int i = lane; i < L; i += 32) out[i] = out[i] / srsum;   // each lane re-reads its own values
 }
